@@ -1,0 +1,192 @@
+/* karma_b200.h -- C ABI of libkarma_b200.so (sm_100a).
+ *
+ * B200-native replacement for ONE hot path of lmfaber/karma: the per-contig
+ * k-mer profile matrix of karma/kmer.py and the exact kNN graph over it.
+ * The reference is pure Python and has NO FFI of its own; every entry point
+ * below therefore cites the Python function it replaces (paths relative to the
+ * reference tree, /root/reference/karma/).  INTEGRATION.md shows the ctypes
+ * binding a karma maintainer would add.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no exceptions, no Python/torch types.
+ *  - every function returns 0 on success or a negative KB_E* code; the text of
+ *    the last error on the calling thread is at kb_last_error().
+ *  - "d_" pointers are device memory on the context's GPU, "h_" pointers host.
+ *  - all work is enqueued on the context's stream (kb_set_stream); functions
+ *    that return values to the host synchronise that stream first and say so.
+ *  - a context is not thread-safe; distinct contexts are independent.
+ *  - there is NO CPU fallback: without a usable sm_100 GPU kb_create fails.
+ */
+#ifndef KARMA_B200_H
+#define KARMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KB_API __attribute__((visibility("default")))
+#else
+#define KB_API
+#endif
+
+typedef struct kb_ctx kb_ctx;
+
+/* error codes */
+#define KB_OK            0
+#define KB_EINVAL       -1   /* bad argument                                  */
+#define KB_ECUDA        -2   /* CUDA runtime/driver error (see kb_last_error) */
+#define KB_ENOGPU       -3   /* no sm_100 device                               */
+#define KB_EUNSUPPORTED -4   /* valid request this build cannot serve          */
+#define KB_EWORKSPACE   -5   /* workspace too small                            */
+#define KB_EOVERFLOW    -6   /* a count exceeds what the kNN operand can hold exactly */
+
+/* column modes (what the count matrix columns mean)
+ *  KB_MODE_5P6       kmer.py's default "-k 5p6": 5-mers + STRING-palindromic
+ *                    6-mers (kmer.py:46-54,69-81), columns in kmer.py's
+ *                    sorted() order over ACGT (kmer.py:172-177): 1088 columns.
+ *  KB_MODE_DENSE_5_6 1024 5-mer codes then 4096 6-mer codes (5120 columns);
+ *                    the north-star throughput shape, NOT kmer.py's columns.
+ *  KB_MODE_DENSE_4_5 256 + 1024 = 1280 columns.
+ *  KB_MODE_K(k)      integer k (kmer.py:83-85), 4^k columns in code order
+ *                    (== sorted() order for ACGT), 1 <= k <= 7.
+ * Codes are base-4 big-endian with A=0 C=1 G=2 T=3 (uppercase only: kmer.py
+ * has no alphabet, any other byte makes an "exotic" window, see kb_count). */
+#define KB_MODE_5P6        0
+#define KB_MODE_DENSE_5_6  1
+#define KB_MODE_DENSE_4_5  2
+#define KB_MODE_K(k)       (16 + (k))
+
+/* kNN implementations */
+#define KB_KNN_AUTO   0
+#define KB_KNN_SIMT   1   /* CUDA-core tile kernel (checker / small inputs)    */
+#define KB_KNN_TC     2   /* tcgen05 + TMA + TMEM distance GEMM, fused top-k   */
+
+KB_API int         kb_version(void);
+KB_API const char* kb_last_error(void);
+
+/* Number of count-matrix columns of a mode, or KB_EINVAL. */
+KB_API int kb_mode_columns(int mode);
+
+/* Context bound to one GPU (one process per GPU).  Fails with KB_ENOGPU when
+ * the device is absent or is not compute capability 10.x. */
+KB_API int kb_create(kb_ctx** out, int device);
+KB_API int kb_destroy(kb_ctx* ctx);
+/* cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream). */
+KB_API int kb_set_stream(kb_ctx* ctx, void* cuda_stream);
+
+/* ---- K1: counting ---------------------------------------------------------
+ * Replaces KmerClustering.__count_kmer_occurence (kmer.py:56-92) and the
+ * window enumeration __kmers_of_seq (kmer.py:181-197) for ACGT-only windows.
+ *
+ *  d_bases    uint8[total]  the sequences' bytes back to back (values of the
+ *                           dict karma.py:40-61 builds); the allocation must be
+ *                           16-byte aligned and readable up to
+ *                           round_up(total,16)+16 bytes.
+ *  d_offsets  int64[n+1]    contig i is bases[offsets[i] .. offsets[i+1])
+ *  d_counts   uint32[n*ld]  out: row i = counts of contig i, columns per mode;
+ *                           fully overwritten (no need to zero).  ld >= D.
+ *  d_exotic   uint32[n]     out (nullable): windows of contig i that contain a
+ *                           byte other than A/C/G/T.  kmer.py gives such windows
+ *                           their own string-keyed columns; they are NOT counted
+ *                           in d_counts (see kb_exotic_*).
+ *  d_presence uint32[D]     out (nullable): non-zero iff the column is non-zero
+ *                           in some row (kmer.py:146-179 "observed k-mers");
+ *                           must be zeroed by the caller (accumulates, so a
+ *                           multi-call / multi-rank OR is possible).
+ * Contigs longer than an internal threshold are split across CTAs and merged.
+ */
+KB_API int kb_count(kb_ctx* ctx, int mode,
+             const uint8_t* d_bases, const int64_t* d_offsets, int64_t n,
+             uint32_t* d_counts, int64_t ld,
+             uint32_t* d_exotic, uint32_t* d_presence);
+
+/* Totals of the most recent kb_count on this context (synchronises the stream):
+ * number of contigs that took the long-contig split path and the sum of d_exotic. */
+KB_API int kb_count_stats(kb_ctx* ctx, int64_t* n_long, int64_t* exotic_total);
+
+/* ---- K1x: exotic windows ---------------------------------------------------
+ * kmer.py has no alphabet (kmer.py:72-73): 'N', lowercase, '\r' ... make their
+ * own k-mer columns, ordered by Python string comparison.  kb_exotic_collect
+ * enumerates every window with a non-ACGT byte, packs it as a 54-bit key
+ * (6 x 9 bits, big-endian, byte+1, zero padded: key order == string order),
+ * and reduces to unique keys and (row,key) counts, all on the GPU.
+ * Synchronises the stream.  n_keys / n_entries are written to the host.      */
+KB_API int kb_exotic_collect(kb_ctx* ctx, int mode,
+                      const uint8_t* d_bases, const int64_t* d_offsets, int64_t n,
+                      const uint32_t* d_exotic,
+                      int64_t* n_keys, int64_t* n_entries);
+/* Copy results of the last kb_exotic_collect to host arrays:
+ *  h_keys  uint64[n_keys] ascending;  entries sorted by (key,row):
+ *  h_entry_row int32, h_entry_key int32 (index into h_keys), h_entry_count uint32 */
+KB_API int kb_exotic_fetch(kb_ctx* ctx, uint64_t* h_keys,
+                    int32_t* h_entry_row, int32_t* h_entry_key, uint32_t* h_entry_count);
+/* Scatter the collected entries into a count matrix:
+ *  d_key_col int32[n_keys] destination column of each unique key. */
+KB_API int kb_exotic_scatter(kb_ctx* ctx, const int32_t* d_key_col,
+                      uint32_t* d_counts, int64_t ld);
+
+/* ---- K2: column compaction -------------------------------------------------
+ * Replaces the sorted(set) column dictionary of __extract_kmers
+ * (kmer.py:146-179): out[:, colmap[c]] = in[:, c] for colmap[c] >= 0; columns
+ * of `out` that no source maps to are zero-filled. */
+KB_API int kb_compact(kb_ctx* ctx, const uint32_t* d_in, int64_t ld_in, int32_t d_cols_in,
+               const int32_t* d_colmap, int64_t n,
+               uint32_t* d_out, int64_t ld_out, int32_t d_cols_out);
+
+/* ---- K3: normalise / convert ----------------------------------------------
+ * Replaces fill_array_for_contig + the scatter loop (kmer.py:108-122,
+ * :206-233): profile[i,c] = (double)count[i,c] / (double)key_len[i], where
+ * key_len[i] = len(header key incl. '>') (kmer.py:213).  Also emits what the
+ * kNN consumes.  Any output may be NULL.
+ *  d_profile  double[n*ld_profile]
+ *  d_operand  fp16 [n*ld_operand]   raw counts as fp16 (exact <= 2048), columns
+ *                                   [d_cols, ld_operand) zero-filled;
+ *                                   ld_operand % 64 == 0
+ *  d_sqnorm   double[n]             sum_c count^2 (exact integer)
+ *  d_rowflag  uint8[n]              bit0: some count > 2048 (operand saturated),
+ *                                   bit1: sqnorm >= 2^24 (fp32 Gram not exact),
+ *                                   bit2: all-zero row (kmer.py:250-258 exits) */
+KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32_t d_cols,
+                 const int32_t* d_key_len, int64_t n,
+                 double* d_profile, int64_t ld_profile,
+                 void* d_operand, int64_t ld_operand,
+                 double* d_sqnorm, uint8_t* d_rowflag);
+
+/* ---- K4 + K5: exact kNN ----------------------------------------------------
+ * Replaces the neighbour search inside umap.UMAP(...).fit_transform at
+ * kmer.py:285-290 (euclidean metric over the profile rows, the point itself
+ * included as neighbour 0).  Queries are a row range of the (possibly
+ * all-gathered) key set: query q is key row q_row0 + q.
+ *
+ * Candidate search: integer Gram matrix of the raw counts on the tensor cores
+ * (fp16 in, fp32 accumulate: exact while counts <= 2048 and sqnorm < 2^24),
+ * distances by norm expansion, per-row running top-k' in the epilogue.
+ * Then K5 reranks the k' candidates exactly:
+ *   d2 = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2     (fp64)
+ * and orders by (self first, d2, index).  d_dist receives sqrt(d2) as float
+ * (UMAP's knn_dists), d_d2 (nullable) the fp64 squared distances.
+ * Rows whose KB rowflag bits 0/1 are set are rejected with KB_EOVERFLOW unless
+ * the exact side path is enabled (see kb_knn_flags).                          */
+KB_API int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl);
+KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
+           const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
+           const int32_t* d_key_len, const double* d_sqnorm, const uint8_t* d_rowflag,
+           int64_t nk, int64_t q_row0, int64_t nq,
+           int32_t* d_idx, float* d_dist, double* d_d2,
+           void* d_workspace, int64_t workspace_bytes);
+
+/* Per-kernel device times (ms) of the most recent call of each stage, measured
+ * with CUDA events on the context stream when timing is enabled.
+ *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank */
+KB_API int kb_enable_timing(kb_ctx* ctx, int on);
+KB_API int kb_last_ms(kb_ctx* ctx, int which, float* ms);   /* synchronises */
+/* Number of kernels this library launched since the context was created. */
+KB_API int64_t kb_launch_count(kb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KARMA_B200_H */

@@ -1,0 +1,72 @@
+// kb_common.cuh -- shared declarations for libkarma_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/karma_b200.h"
+
+#define KB_N_TIMERS 8
+
+struct kb_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    int timing;
+    cudaEvent_t ev0[KB_N_TIMERS], ev1[KB_N_TIMERS];
+    int ev_valid[KB_N_TIMERS];
+    int64_t launches;
+    // K1 scratch: work counter + long-contig list
+    int32_t* d_k1_scratch;          // [0] contig counter, [1] n_long, [2..] long ids
+    int64_t k1_scratch_cap;         // capacity in int32 entries
+    // exotic side path (owned)
+    uint64_t* d_ex_keys;            // unique keys
+    int32_t* d_ex_row; int32_t* d_ex_keyidx; uint32_t* d_ex_cnt;
+    int64_t ex_n_keys, ex_n_entries;
+    // tensor-map encoder (driver entry point, resolved lazily)
+    void* encode_tiled;
+};
+
+void kb_set_error(const char* fmt, ...);
+int kb_cuda_fail(cudaError_t e, const char* what);
+
+#define KB_CUDA(call)                                                   \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return kb_cuda_fail(_e, #call);          \
+    } while (0)
+
+#define KB_CHECK_ARG(cond, msg)                                         \
+    do {                                                                \
+        if (!(cond)) { kb_set_error("invalid argument: %s", msg); return KB_EINVAL; } \
+    } while (0)
+
+struct KbTimer {
+    kb_ctx* c; int which;
+    KbTimer(kb_ctx* ctx, int w) : c(ctx), which(w) {
+        if (c->timing) cudaEventRecord(c->ev0[which], c->stream);
+    }
+    ~KbTimer() {
+        if (c->timing) { cudaEventRecord(c->ev1[which], c->stream); c->ev_valid[which] = 1; }
+    }
+};
+
+// mode description shared by host and device
+struct KbMode {
+    int ka;        // first component k (0 = none)
+    int kb;        // second component k (0 = none)
+    int pal_b;     // second component: string-palindromic windows only, binned by rank
+    int bins_a;    // 4^ka
+    int bins_b;    // 4^kb, or 4^(kb/2) when pal_b
+    int permute;   // columns are a permutation of [A bins | B bins] (5p6 sorted order)
+    int cols;      // bins_a + bins_b
+};
+int kb_mode_describe(int mode, KbMode* out);
+
+// internal launchers (defined in the per-kernel .cu files)
+int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases,
+                            const int64_t* d_offsets, int64_t n, uint32_t* d_counts,
+                            int64_t ld, uint32_t* d_exotic, uint32_t* d_presence);
+
+static inline int64_t kb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -1,0 +1,341 @@
+// kb_knn_tc.cu -- K4: distance GEMM on tcgen05 tensor cores with a fused per-row
+// top-k' epilogue (sm_100a only).
+//
+// Replaces the O(N^2 D) neighbour search inside umap.UMAP(...).fit_transform at
+// /root/reference/karma/kmer.py:285-290.
+//
+//   G = C_q * C_k^T     C = raw k-mer counts as fp16 (exact <= 2048), fp32 accumulate
+//                       in TMEM (exact integer Gram while sum c^2 < 2^24)
+//   score_ij = fma(G_ij, -2/l_j, l_i * n_j/l_j^2)   ( = l_i*d2_ij - n_i/l_i )
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0      TMA producer: 128x64 (A) and 2 x 128x64 (B) fp16 boxes, SWIZZLE_128B,
+//               STAGES-deep mbarrier ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//               (cta_group::1, kind::f16, M=128 N=256 K=16), accumulators double
+//               buffered in TMEM (2 x 256 columns)
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns, one thread per query
+//               row; running top-KP list per row in shared memory
+// Work unit = (128-row query block) x (split of the key tiles); each unit writes
+// KP candidates per row, merged and exactly reranked by K5 (kb_knn.cu).
+//
+// Roofline: tensor pipe.  Algorithmic flops = 2 * nq * nk * D.
+#include "kb_knn.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t it = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++it & 0x3ff) == 0 && clock64() - t0 > 6000000000LL) {
+            printf("kb_knn_tc: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// rows are 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address          [0,14)
+    d |= (uint64_t)1 << 16;                              // leading byte offset    [16,30) (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset     [32,46)
+    d |= (uint64_t)1 << 46;                              // descriptor version     [46,48)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B           [61,64)
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=F32, A=B=F16, K-major both, N=256, M=128
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct TcParams {
+    int64_t nk, q_row0, nq;
+    int64_t m_blocks, n_tiles;
+    int splits;
+    int k_blocks;                     // Dp / 64
+    const float2* colmeta;
+    const int32_t* key_len;
+    float* cand_score;
+    int32_t* cand_idx;
+};
+
+template <int KP, int STAGES>
+struct Smem {
+    static constexpr int OFF_STAGES = 0;
+    static constexpr int OFF_LIST_S = STAGES * STAGE_BYTES;
+    static constexpr int OFF_LIST_I = OFF_LIST_S + KP * BM * 4;
+    static constexpr int OFF_COLMETA = OFF_LIST_I + KP * BM * 4;
+    static constexpr int OFF_BARS = OFF_COLMETA + BN * 8;
+    // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+    static constexpr int OFF_TMEM_SLOT = OFF_BARS + (2 * STAGES + 4) * 8;
+    static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
+};
+
+template <int KP, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    using L = Smem<KP, STAGES>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && (sbase & 1023u)) {
+        printf("kb_knn_tc: dynamic shared memory is not 1024-byte aligned (0x%x)\n", sbase);
+        __trap();
+    }
+    const uint32_t bar_full = sbase + L::OFF_BARS;
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 2 * 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::OFF_TMEM_SLOT);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_units = p.m_blocks * p.splits;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int64_t mb = u % p.m_blocks; const int s = (int)(u / p.m_blocks);
+                const int64_t t_lo = p.n_tiles * s / p.splits, t_hi = p.n_tiles * (s + 1) / p.splits;
+                const int32_t arow = (int32_t)(p.q_row0 + mb * BM);
+                for (int64_t t = t_lo; t < t_hi; ++t) {
+                    const int32_t brow = (int32_t)(t * BN);
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+                        const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE_BYTES;
+                        const uint32_t fb = bar_full + 8 * stage;
+                        mbar_expect_tx(fb, STAGE_BYTES);
+                        tma_load_2d(sa, &tmap, kb * BK, arow, fb);
+                        tma_load_2d(sa + A_BYTES, &tmap, kb * BK, brow, fb);
+                        tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, kb * BK, brow + 128, fb);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int s = (int)(u / p.m_blocks);
+                const int64_t t_lo = p.n_tiles * s / p.splits, t_hi = p.n_tiles * (s + 1) / p.splits;
+                for (int64_t t = t_lo; t < t_hi; ++t) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase, 3);
+                        tc_fence_after();
+                        const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE_BYTES;
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 B per K=16 step inside the 128 B swizzle atom (>>4 => +2)
+                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+                        }
+                        umma_commit(bar_empty + 8 * stage);          // frees the smem stage when the MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + 8 * acc);                // accumulator ready for the epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: warps 2..5 =================
+        const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
+        const int r = quad * 32 + lane;                      // row of the 128-row tile
+        const int et = threadIdx.x - 64;                     // 0..127
+        KbRowList<KP, BM> list{reinterpret_cast<float*>(smem + L::OFF_LIST_S),
+                               reinterpret_cast<int32_t*>(smem + L::OFF_LIST_I)};
+        float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int64_t mb = u % p.m_blocks; const int s = (int)(u / p.m_blocks);
+            const int64_t t_lo = p.n_tiles * s / p.splits, t_hi = p.n_tiles * (s + 1) / p.splits;
+            const int64_t q = mb * BM + r;
+            const float li = (q < p.nq) ? (float)p.key_len[p.q_row0 + q] : 1.f;
+            list.init(r);
+            float thr = __int_as_float(0x7f800000); int pos = 0;
+            for (int64_t t = t_lo; t < t_hi; ++t) {
+                const int64_t n0 = t * BN;
+                // stage this tile's key metadata (all 128 epilogue threads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cm_s[et] = p.colmeta[n0 + et];
+                cm_s[et + 128] = p.colmeta[n0 + et + 128];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(bar_tfull + 8 * acc, acc_phase, 4);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) {
+                        const float sc = kb_score(__uint_as_float(v[x]), cm_s[c * 32 + x], li);
+                        if (sc < thr) list.insert(r, sc, (int32_t)(n0 + c * 32 + x), thr, pos);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (q < p.nq) {
+                const int64_t base = (q * p.splits + s) * KP;
+#pragma unroll
+                for (int e = 0; e < KP; ++e) {
+                    p.cand_score[base + e] = list.s[e * BM + r];
+                    p.cand_idx[base + e] = list.i[e * BM + r];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int KP, int STAGES>
+int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int64_t n_units) {
+    using L = Smem<KP, STAGES>;
+    auto kern = k4_tc<KP, STAGES>;
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    const int64_t grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
+    kern<<<(unsigned)grid, NUM_THREADS, L::TOTAL, ctx->stream>>>(tmap, prm);
+    ctx->launches++;
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+}  // namespace
+
+int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int64_t ld_operand,
+                     int32_t d_cols_padded, const int32_t* d_key_len, int64_t nk, int64_t q_row0,
+                     int64_t nq, uint8_t* ws) {
+    if (!ctx->encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        KB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { kb_set_error("cuTensorMapEncodeTiled not available from the driver"); return KB_ECUDA; }
+        ctx->encode_tiled = fn;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d_cols_padded, (cuuint64_t)nk};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld_operand * 2};
+    const cuuint32_t box[2] = {BK, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_operand),
+                                                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { kb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return KB_ECUDA; }
+    TcParams prm;
+    prm.nk = nk; prm.q_row0 = q_row0; prm.nq = nq;
+    prm.m_blocks = p.m_blocks; prm.n_tiles = p.n_tiles; prm.splits = p.splits;
+    prm.k_blocks = d_cols_padded / BK;
+    prm.colmeta = reinterpret_cast<const float2*>(ws + p.off_colmeta);
+    prm.key_len = d_key_len;
+    prm.cand_score = reinterpret_cast<float*>(ws + p.off_score);
+    prm.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
+    const int64_t n_units = p.m_blocks * p.splits;
+    switch (p.kp) {
+        case 8: return launch_tc<8, 4>(ctx, tmap, prm, n_units);
+        case 16: return launch_tc<16, 4>(ctx, tmap, prm, n_units);
+        default: return launch_tc<32, 4>(ctx, tmap, prm, n_units);
+    }
+}

@@ -1,0 +1,352 @@
+"""Host pipeline over the C ABI: pack -> K1 count -> (K1x/K2) -> K3 -> K4/K5.
+
+PyTorch is used only as plumbing: device/pinned allocations, streams, and
+``torch.distributed`` (NCCL) for the one exchange step of the kNN (all-gather
+of the operand shards).  All arithmetic happens inside libkarma_b200.so.
+
+Column dictionary (kmer.py:146-179).  kmer.py's columns are the k-mer strings
+that occur anywhere in the input, in ``sorted()`` order.  The GPU counts into
+the full ACGT code space (already in sorted order) and reports which columns
+are present; this module turns presence bits (+ the keys of non-ACGT windows
+from K1x) into the column list and a compaction map.  That is dictionary
+bookkeeping over <= a few thousand strings, not a compute fallback.
+"""
+import ctypes
+from ctypes import byref, c_float, c_int64, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KB_KNN_AUTO, KB_MODE_5P6, KB_MODE_DENSE_4_5, KB_MODE_DENSE_5_6, KB_MODE_K, check, ptr
+
+_BASES = "ACGT"
+
+
+def mode_of(kmer_size):
+    """kmer.py's kmer_size ("5p6" or int) or a dense-mode name -> KB_MODE_*."""
+    if kmer_size == "5p6":
+        return KB_MODE_5P6
+    if kmer_size == "5+6":
+        return KB_MODE_DENSE_5_6
+    if kmer_size == "4+5":
+        return KB_MODE_DENSE_4_5
+    if isinstance(kmer_size, (int, np.integer)) and not isinstance(kmer_size, bool):
+        if not 1 <= int(kmer_size) <= 7:
+            raise _lib.KarmaB200Error(-4, "integer k-mer sizes 1..7 are built (got %r)" % (kmer_size,))
+        return KB_MODE_K(int(kmer_size))
+    # same failure kmer.py produces for e.g. "4p5": len(seq) - "4p5" -> TypeError (kmer.py:84)
+    raise TypeError("unsupported operand type(s) for -: 'int' and %r" % type(kmer_size).__name__)
+
+
+def _kmer(code, k):
+    return "".join(_BASES[(code >> (2 * (k - 1 - t))) & 3] for t in range(k))
+
+
+_names_cache = {}
+
+
+def mode_column_names(mode):
+    """Names of the fixed ACGT columns of a mode, in column order."""
+    if mode in _names_cache:
+        return _names_cache[mode]
+    if mode == KB_MODE_5P6:
+        # sorted(5-mers U string-palindromic 6-mers), kmer.py:172: x1x2x3x3x2x1 follows x1x2x3x3x2
+        names = []
+        for c in range(1024):
+            s = _kmer(c, 5)
+            names.append(s)
+            if s[3] == s[2] and s[4] == s[1]:
+                names.append(s + s[0])
+    elif mode == KB_MODE_DENSE_5_6:
+        names = [_kmer(c, 5) for c in range(1024)] + [_kmer(c, 6) for c in range(4096)]
+    elif mode == KB_MODE_DENSE_4_5:
+        names = [_kmer(c, 4) for c in range(256)] + [_kmer(c, 5) for c in range(1024)]
+    else:
+        k = mode - 16
+        names = [_kmer(c, k) for c in range(4 ** k)]
+    _names_cache[mode] = names
+    return names
+
+
+def decode_exotic_key(key):
+    """63-bit key of kb_exotic_collect -> the k-mer string (latin-1 bytes)."""
+    out = []
+    for t in range(7):
+        v = (int(key) >> (9 * (6 - t))) & 511
+        if v == 0:
+            break
+        out.append(chr(v - 1))
+    return "".join(out)
+
+
+def shard_bounds(n_total, world, rank):
+    """Contiguous row shard of ``rank``: blocks of per=ceil(n/world) rows, so that the
+    index of a row in the zero-padded all-gathered key set equals its global index."""
+    per = -(-n_total // world) if n_total else 0
+    lo = min(rank * per, n_total)
+    hi = min(lo + per, n_total)
+    return lo, hi, per
+
+
+def merge_columns(names, present, exotic_names):
+    """kmer.py:172-177: the column list is sorted(observed k-mer strings).
+    names/present describe the fixed ACGT columns (already in sorted order);
+    exotic_names are the k-mers with non-ACGT characters (any order, unique).
+    Returns (columns, colmap int32[len(names)], keycol int32[len(exotic_names)])."""
+    present = np.asarray(present, dtype=bool)
+    merged = sorted([(names[i], 0, int(i)) for i in np.flatnonzero(present)] +
+                    [(s, 1, j) for j, s in enumerate(exotic_names)])
+    columns = [m[0] for m in merged]
+    colmap = np.full(len(names), -1, dtype=np.int32)
+    keycol = np.full(len(exotic_names), -1, dtype=np.int32)
+    for dst, (_, kind, src) in enumerate(merged):
+        if kind == 0:
+            colmap[src] = dst
+        else:
+            keycol[src] = dst
+    return columns, colmap, keycol
+
+
+def all_gather_padded(t, n, per, group, fill=0):
+    """All-gather row shards of unequal length: rows [0,n) of ``t`` are padded to
+    ``per`` rows with ``fill`` and gathered into (per*world, ...).  Works for any
+    backend/device (NCCL on GPU, gloo on CPU)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    pad = torch.full((per,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+    pad[:n] = t[:n]
+    out = torch.empty((per * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out
+
+
+class ZeroRowError(Exception):
+    """A contig shorter than k: kmer.py logs an error and exit(1)s (kmer.py:250-258)."""
+
+    def __init__(self, row):
+        super().__init__("Values of row %d are all zero, which should not be the case." % row)
+        self.row = row
+
+
+class Engine:
+    """One GPU, one context.  Not thread-safe."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.KarmaB200Error(_lib.KB_ENOGPU, "no CUDA device visible: karma_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        h = c_void_p()
+        check(self.lib.kb_create(byref(h), self.device_index))
+        self.ctx = h
+        self._ws = None
+        self._bind_stream()
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.kb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _bind_stream(self):
+        check(self.lib.kb_set_stream(self.ctx, c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    # ---- timing / accounting -------------------------------------------------
+    def enable_timing(self, on=True):
+        check(self.lib.kb_enable_timing(self.ctx, 1 if on else 0))
+
+    def last_ms(self, stage):
+        ms = c_float()
+        check(self.lib.kb_last_ms(self.ctx, _lib.STAGES[stage], byref(ms)))
+        return ms.value
+
+    def launches(self):
+        return int(self.lib.kb_launch_count(self.ctx))
+
+    # ---- uploads ---------------------------------------------------------------
+    def upload(self, bases, offsets, key_len, pinned=False):
+        """Host arrays -> device tensors.  ``bases`` is padded so that the kernel's
+        aligned 128-bit loads stay inside the allocation."""
+        total = int(offsets[-1])
+        cap = (total + 15) // 16 * 16 + 32
+        d_bases = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        hb = bases if isinstance(bases, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bases))
+        ho = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
+        hk = key_len if isinstance(key_len, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(key_len, dtype=np.int32))
+        d_bases[:total].copy_(hb[:total], non_blocking=True)
+        d_offsets = ho.to(self.device, non_blocking=True)
+        d_key_len = hk.to(self.device, non_blocking=True)
+        return d_bases, d_offsets, d_key_len
+
+    # ---- K1 ----------------------------------------------------------------------
+    def count(self, d_bases, d_offsets, n, mode, counts=None, exotic=None, presence=None):
+        """u32 counts (n, D) [torch.int32 storage], exotic tallies (n,), presence (D,)."""
+        self._bind_stream()
+        cols = check(self.lib.kb_mode_columns(mode))
+        if counts is None:
+            counts = torch.empty((n, cols), dtype=torch.int32, device=self.device)
+        if exotic is None:
+            exotic = torch.empty(n, dtype=torch.int32, device=self.device)
+        if presence is None:
+            presence = torch.empty(cols, dtype=torch.int32, device=self.device)
+        presence.zero_()
+        check(self.lib.kb_count(self.ctx, mode, ptr(d_bases), ptr(d_offsets), n, ptr(counts), counts.stride(0),
+                                ptr(exotic), ptr(presence)))
+        return counts, exotic, presence
+
+    def count_stats(self):
+        nl, ex = c_int64(), c_int64()
+        check(self.lib.kb_count_stats(self.ctx, byref(nl), byref(ex)))
+        return nl.value, ex.value
+
+    # ---- K1x / K2: column dictionary ---------------------------------------------
+    def build_columns(self, mode, d_bases, d_offsets, n, counts, exotic, presence, exotic_total,
+                      group=None):
+        """kmer.py:146-179.  Returns (columns, counts') where columns is the sorted
+        list of observed k-mer strings and counts' the (n, D') matrix in that order."""
+        self._bind_stream()
+        names = mode_column_names(mode)
+        pres = presence
+        if group is not None:
+            import torch.distributed as dist
+            pres = presence.clone()
+            dist.all_reduce(pres, op=dist.ReduceOp.MAX, group=group)
+            t = torch.tensor([exotic_total], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            any_exotic = int(t.item()) > 0
+        else:
+            any_exotic = exotic_total > 0
+        present = pres.cpu().numpy() != 0
+        keys = np.zeros(0, dtype=np.uint64)
+        if any_exotic:
+            nk, ne = c_int64(), c_int64()
+            check(self.lib.kb_exotic_collect(self.ctx, mode, ptr(d_bases), ptr(d_offsets), n, ptr(exotic),
+                                             byref(nk), byref(ne)))
+            keys = np.empty(nk.value, dtype=np.uint64)
+            if nk.value:
+                check(self.lib.kb_exotic_fetch(self.ctx, keys.ctypes.data_as(c_void_p), None, None, None))
+            if group is not None:
+                import torch.distributed as dist
+                gathered = [None] * dist.get_world_size(group)
+                dist.all_gather_object(gathered, keys, group=group)
+                all_keys = np.unique(np.concatenate(gathered)) if gathered else keys
+            else:
+                all_keys = keys
+        else:
+            all_keys = keys
+        if present.all() and len(all_keys) == 0:
+            return list(names), counts
+        exo_names = [decode_exotic_key(k) for k in all_keys]
+        columns, colmap, keycol_all = merge_columns(names, present, exo_names)
+        d_out = len(columns)
+        ld_out = max(4, (d_out + 3) // 4 * 4)
+        out = torch.empty((n, ld_out), dtype=torch.int32, device=self.device)
+        d_colmap = torch.from_numpy(colmap).to(self.device)
+        check(self.lib.kb_compact(self.ctx, ptr(counts), counts.stride(0), counts.shape[1], ptr(d_colmap), n,
+                                  ptr(out), ld_out, d_out))
+        if len(keys):
+            # local unique keys -> destination columns
+            pos = np.searchsorted(all_keys, keys)
+            d_keycol = torch.from_numpy(keycol_all[pos]).to(self.device)
+            check(self.lib.kb_exotic_scatter(self.ctx, ptr(d_keycol), ptr(out), ld_out))
+        return columns, out[:, :d_out]
+
+    # ---- K3 ------------------------------------------------------------------------
+    def normalise(self, counts, d_cols, d_key_len, want_profile=True, want_operand=True, profile=None):
+        self._bind_stream()
+        n = counts.shape[0]
+        ldp = d_cols
+        if want_profile and profile is None:
+            profile = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
+        dp = (d_cols + 63) // 64 * 64
+        operand = torch.empty((n, dp), dtype=torch.float16, device=self.device) if want_operand else None
+        sqnorm = torch.empty(n, dtype=torch.float64, device=self.device)
+        rowflag = torch.empty(n, dtype=torch.uint8, device=self.device)
+        check(self.lib.kb_normalise(self.ctx, ptr(counts), counts.stride(0), d_cols, ptr(d_key_len), n,
+                                    ptr(profile) if want_profile else None, ldp,
+                                    ptr(operand), dp, ptr(sqnorm), ptr(rowflag)))
+        return profile, operand, sqnorm, rowflag
+
+    # ---- K4 + K5 ---------------------------------------------------------------------
+    def knn(self, operand, key_len, sqnorm, rowflag, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False):
+        self._bind_stream()
+        nk, dp = operand.shape
+        nq = nk - q_row0 if nq is None else nq
+        need = check(self.lib.kb_knn_workspace_bytes(nq, nk, k, impl))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        d2 = torch.empty((nq, k), dtype=torch.float64, device=self.device) if want_d2 else None
+        check(self.lib.kb_knn(self.ctx, impl, k, ptr(operand), operand.stride(0), dp, ptr(key_len), ptr(sqnorm),
+                              ptr(rowflag), nk, q_row0, nq, ptr(idx), ptr(dist), ptr(d2),
+                              ptr(self._ws), self._ws.numel()))
+        return idx, dist, d2
+
+
+# ---------------------------------------------------------------------------------------
+# whole path, host in -> host out  (what KmerClustering and bench.py's e2e leg call)
+# ---------------------------------------------------------------------------------------
+
+def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbors=None,
+                    impl=KB_KNN_AUTO, want_profile=True, group=None, rank=0, world=1, row0=0, n_total=None):
+    """Run the hot path on host buffers.
+
+    bases/offsets/key_len describe THIS rank's contigs (all of them when world==1).
+    Returns dict(columns, profile (n,D') float64 ndarray or None, knn_idx, knn_dist)
+    where the kNN rows are this rank's contigs against ALL contigs (global indices).
+    Raises ZeroRowError when a contig is shorter than k (kmer.py:250-258).
+    """
+    mode = mode_of(kmer_size)
+    n = len(offsets) - 1
+    d_bases, d_offsets, d_key_len = engine.upload(bases, offsets, key_len)
+    counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode)
+    faithful = mode == KB_MODE_5P6 or mode >= 16
+    _, ex_total = engine.count_stats()
+    if faithful:
+        columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence, ex_total,
+                                               group=group)
+    else:
+        if ex_total:
+            raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (%d windows contain other bytes)" % ex_total)
+        columns = mode_column_names(mode)
+    d_cols = len(columns)
+    if d_cols == 0:
+        raise ZeroRowError(0)
+    if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
+        counts = counts.contiguous()
+    profile, operand, sqnorm, rowflag = engine.normalise(counts, d_cols, d_key_len, want_profile=want_profile,
+                                                         want_operand=n_neighbors is not None)
+    flags = rowflag.cpu().numpy()
+    zero = np.flatnonzero(flags & 4)
+    if len(zero):
+        raise ZeroRowError(int(zero[0]) + row0)
+    out = {"columns": columns, "profile": None, "knn_idx": None, "knn_dist": None,
+           "d_profile": profile, "d_operand": operand}
+    if n_neighbors is not None:
+        if (flags & 3).any():
+            raise _lib.KarmaB200Error(-6, "a k-mer count > 2048 or a squared norm >= 2^24 needs the exact side path (not built yet)")
+        if group is not None and world > 1:
+            # the one exchange step: every rank needs all keys (operand + row metadata);
+            # padding rows are flagged so they can never be candidates
+            _, _, per = shard_bounds(n_total, world, rank)
+            all_op = all_gather_padded(operand, n, per, group, 0)
+            all_len = all_gather_padded(d_key_len, n, per, group, 1)
+            all_sq = all_gather_padded(sqnorm, n, per, group, 0)
+            all_fl = all_gather_padded(rowflag, n, per, group, 3)
+            idx, dst, _ = engine.knn(all_op, all_len, all_sq, all_fl, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
+        else:
+            idx, dst, _ = engine.knn(operand, d_key_len, sqnorm, rowflag, n_neighbors, impl=impl)
+        out["knn_idx"] = idx.cpu().numpy()
+        out["knn_dist"] = dst.cpu().numpy()
+    if want_profile:
+        out["profile"] = profile.cpu().numpy()
+    return out

@@ -1,0 +1,201 @@
+"""Drop-in mirror of ``karma/kmer.py`` (reference: /root/reference/karma/kmer.py).
+
+Same class, constructor, ``run`` signature, attributes, files and messages as the
+reference's ``KmerClustering`` (kmer.py:14-325); the k-mer profile matrix
+(``__calc_kmer_profile``, kmer.py:199-264) and the neighbour search that
+``umap.UMAP(...).fit_transform`` performs first (kmer.py:285-290) run on a B200
+through libkarma_b200.so.  There is no CPU path: without the GPU library the
+profile step raises ``KarmaB200Error``.
+
+karma.py keeps doing (karma.py:197-213)::
+
+    k = KmerClustering(sequences=sequences, output_dir=kmer_dir,
+                       kmer_size=args.KMER_SIZE, threads=args.THREADS)
+    k.run(neighbors=..., components=..., dist=..., r_state=..., min_cluster_size=...)
+    labeled_contigs = k.clusters; unlabeled_contigs = k.unlabeled_cluster[0]
+"""
+import logging
+import os
+import sys
+
+import numpy as np
+
+try:                                    # inside karma: the shared logger (kmer.py:11)
+    from karma.logs import logger
+except Exception:                       # stand-alone: same format as karma/logs.py:9-11
+    logger = logging.getLogger("karma_b200.kmer")
+    if not logger.handlers:
+        _h = logging.StreamHandler()
+        _h.setFormatter(logging.Formatter("{asctime} [{levelname}]: {message}",
+                                          datefmt="%Y-%m-%d %H:%M:%S", style="{"))
+        logger.addHandler(_h)
+    logger.setLevel(logging.INFO)
+
+
+class KmerClustering:
+    def __init__(self, sequences, output_dir, kmer_size, threads):
+        # kmer.py:15-27
+        self.sequences = sequences
+        self.output_dir = output_dir
+        self.output_eval = f"{self.output_dir}/eval.txt"
+        self.output_file = f"{self.output_dir}/cluster.txt"
+
+        self.threads = threads          # kept for interface parity; the GPU path does not fork
+        self.kmer_size = kmer_size
+
+        self.clusters = []
+        self.unlabeled_cluster = []
+        self.kmers = None
+        self.sorted_kmer_set = set()
+
+        # GPU-side products of the last profile computation
+        self.knn_indices = None
+        self.knn_dists = None
+        self._engine = None
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def __mask_list(list_to_mask, mask):
+        """kmer.py:30-44 -- same grouping and ordering (labels in ``set(mask)``
+        iteration order, members in input order) without rebuilding
+        ``list(keys())`` per element (the reference is O(N^2) there)."""
+        names = [k.lstrip(">") for k in list_to_mask.keys()]
+        groups = {}
+        for j, lab in enumerate(mask):
+            groups.setdefault(lab, []).append(names[j])
+        labeled, unlabeled = [], []
+        for i in set(mask):
+            (unlabeled if i == -1 else labeled).append(groups[i])
+        return (labeled, unlabeled)
+
+    @staticmethod
+    def is_palindrome(sequence):
+        """kmer.py:46-54 -- plain string palindrome (not reverse complement)."""
+        return sequence == sequence[::-1]
+
+    def fill_array_for_contig(self, *args):
+        """kmer.py:108-122 -- (row, col, count/length) triples of one contig's Counter.
+        Kept because it is public in the reference; the GPU path does not call it."""
+        row, contig, length = args[0], args[1], args[2]
+        return [(row, self.kmers[kmer], count / length) for kmer, count in contig.items()]
+
+    def __fix_fasta_headers(self):
+        # kmer.py:94-106
+        self.unlabeled_cluster = [[name.split(" ")[0] for name in self.unlabeled_cluster[0]]]
+        renamed_cluster = []
+        for cluster in self.clusters:
+            renamed_cluster.append([name.split(" ")[0] for name in cluster])
+        assert len(renamed_cluster) == len(self.clusters), \
+            "Something went wrong while renaming fasta header. See if removing spaces from fasta headers solves the problem."
+        self.clusters = renamed_cluster
+
+    def __save_groups_to_file(self):
+        # kmer.py:124-133: line 1 = unlabeled, then one cluster per line, tab separated
+        with open(self.output_file, "w") as cluster_writer:
+            cluster_writer.write("\t".join(self.unlabeled_cluster[0]) + "\n")
+            for cluster in self.clusters:
+                cluster_writer.write("\t".join(cluster) + "\n")
+
+    def __read_clusters(self):
+        # kmer.py:135-144
+        with open(self.output_file, "r") as cluster_reader:
+            self.unlabeled_cluster = [cluster_reader.readline().rstrip("\n").split("\t")]
+            for line in cluster_reader:
+                self.clusters.append(line.rstrip("\n").split("\t"))
+
+    def __write_eval_information(self, **kwargs):
+        # kmer.py:266-272
+        with open(f"{self.output_eval}", "w") as writer:
+            writer.write("\t".join(list(kwargs.keys())) + "\n")
+            writer.write("\t".join([str(a) for a in list(kwargs.values())]) + "\n")
+
+    # ------------------------------------------------------------------ GPU path
+    def _pack(self):
+        """dict -> packed buffers of the C ABI.  One byte per character (latin-1):
+        byte order then equals the code-point order ``sorted()`` uses (kmer.py:172)."""
+        seqs = list(self.sequences.values())
+        try:
+            raw = "".join(seqs).encode("latin-1")
+        except UnicodeEncodeError as e:
+            raise ValueError("karma_b200: sequences must be single-byte characters") from e
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+        offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        bases = np.frombuffer(raw, dtype=np.uint8)
+        key_len = np.fromiter((len(k) for k in self.sequences), dtype=np.int32, count=len(seqs))
+        return bases, offsets, key_len
+
+    def _get_engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine()
+        return self._engine
+
+    def __calc_kmer_profile(self, n_neighbors=None):
+        """kmer.py:199-264 on the GPU.  Returns the float64 (N, D) profile; sets
+        ``self.kmers`` ({kmer: column}) like the reference.  With ``n_neighbors``
+        the exact kNN graph is computed in the same pass and left in
+        ``self.knn_indices`` / ``self.knn_dists``."""
+        from .engine import ZeroRowError, profile_and_knn
+        logger.info("Extracting kmers from contigs.")               # kmer.py:152
+        if self.kmer_size != "5p6":
+            logger.info(f"Accounting only {self.kmer_size}-mers.")  # kmer.py:167
+        if len(self.sequences) == 0:
+            self.kmers = {}
+            return np.zeros((0, 0), dtype=np.float64)
+        bases, offsets, key_len = self._pack()
+        try:
+            res = profile_and_knn(self._get_engine(), bases, offsets, key_len, self.kmer_size,
+                                  n_neighbors=n_neighbors)
+        except ZeroRowError as e:
+            # the column dictionary exists by the time the reference fails (kmer.py:202)
+            logger.error(f"Values of row {e.row} are all zero, which should not be the case.")  # kmer.py:255-258
+            sys.exit(1)
+        self.sorted_kmer_set = list(res["columns"])
+        self.kmers = {kmer: i for i, kmer in enumerate(self.sorted_kmer_set)}   # kmer.py:175-177
+        self.knn_indices, self.knn_dists = res["knn_idx"], res["knn_dist"]
+        kmer_profile = res["profile"]
+        self.sorted_kmer_set.clear()                                            # kmer.py:259
+        logger.debug(f"KMER-PROFILE - Size: {sys.getsizeof(kmer_profile)}, Shape: {kmer_profile.shape}")
+        return kmer_profile
+
+    def run(self, neighbors, components, dist, r_state, min_cluster_size):
+        # kmer.py:274-325
+        if os.path.isfile(self.output_file):
+            logger.info(f"Read from previous calculation: {self.output_file}")
+            self.__read_clusters()
+        else:
+            logger.info("Calculate kmer profiles.")
+            kmer_profile = self.__calc_kmer_profile(n_neighbors=neighbors)
+
+            logger.info("Dimension reduction with UMAP.")
+            import umap
+            kwargs = dict(n_neighbors=neighbors, n_components=components, min_dist=dist, random_state=r_state)
+            try:
+                # umap-learn >= 0.5: hand over the exact graph (self in column 0, euclidean distances)
+                reducer = umap.UMAP(precomputed_knn=(self.knn_indices.astype(np.int64), self.knn_dists, None),
+                                    **kwargs).fit_transform(kmer_profile)
+            except TypeError:
+                # umap-learn 0.3.9 (conda/meta.yaml:15) has no such argument: unchanged call (kmer.py:285-290)
+                reducer = umap.UMAP(**kwargs).fit_transform(kmer_profile)
+
+            logger.info(f"Perform clustering with HDBSCAN. (min_cluster_size: {min_cluster_size})")
+            import hdbscan
+            if min_cluster_size == 1:
+                clusterer = hdbscan.HDBSCAN(allow_single_cluster=True).fit(reducer)
+            else:
+                clusterer = hdbscan.HDBSCAN(min_cluster_size=min_cluster_size).fit(reducer)
+
+            self.clusters, self.unlabeled_cluster = self.__mask_list(self.sequences, clusterer.labels_)
+
+            self.__save_groups_to_file()
+
+            no_unlabeled = list(clusterer.labels_).count(-1)
+            no_groups = max(clusterer.labels_) + 1
+            mean_probability = np.mean(clusterer.probabilities_)
+            self.__write_eval_information(
+                kmer_size=self.kmer_size, n_neighbors=neighbors, n_components=components, min_dist=dist,
+                random_state=r_state, min_cluster_size=min_cluster_size, unlabeled=no_unlabeled,
+                no_groups=no_groups, mean_probability=mean_probability)
+
+        self.__fix_fasta_headers()

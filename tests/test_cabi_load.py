@@ -1,0 +1,74 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"KB_API\s+[\w\s\*]+?\b(kb_\w+)\s*\(", src))
+    return names
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__
+    from karma_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        __graft_entry__.build()
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from karma_b200 import _lib
+    declared = _declared()
+    assert len(declared) >= 18
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+
+
+def test_pure_host_entry_points(lib):
+    from karma_b200 import _lib
+    assert lib.kb_version() >= 100
+    assert lib.kb_mode_columns(_lib.KB_MODE_5P6) == 1088
+    assert lib.kb_mode_columns(_lib.KB_MODE_DENSE_5_6) == 5120
+    assert lib.kb_mode_columns(_lib.KB_MODE_DENSE_4_5) == 1280
+    assert [lib.kb_mode_columns(_lib.KB_MODE_K(k)) for k in range(1, 8)] == [4 ** k for k in range(1, 8)]
+    assert lib.kb_mode_columns(999) < 0 and b"unknown column mode" in lib.kb_last_error()
+    assert lib.kb_knn_workspace_bytes(1000, 1000, 2, 0) > 0
+    assert lib.kb_knn_workspace_bytes(1000, 1000, 200, 0) < 0          # unsupported k is an error, not a fallback
+    assert lib.kb_knn_workspace_bytes(10, 5, 8, 0) < 0                  # k > nk
+
+
+def test_no_cpu_fallback(lib):
+    """Without a GPU the product path must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from karma_b200 import _lib
+    h = ctypes.c_void_p()
+    assert lib.kb_create(ctypes.byref(h), 0) == _lib.KB_ENOGPU
+    assert b"no CPU fallback" in lib.kb_last_error()
+    from karma_b200.engine import Engine
+    with pytest.raises(_lib.KarmaB200Error):
+        Engine()
+    from karma_b200.kmer import KmerClustering
+    k = KmerClustering({">a": "ACGTACGT"}, "/tmp", "5p6", 1)
+    with pytest.raises(_lib.KarmaB200Error):
+        k._KmerClustering__calc_kmer_profile()
+
+
+def test_product_never_imports_oracle():
+    for path in glob.glob(os.path.join(ROOT, "karma_b200", "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), path

@@ -1,0 +1,160 @@
+"""Host-side logic of the drop-in class and the column dictionary (no GPU)."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from karma_b200 import _lib
+from karma_b200.engine import (decode_exotic_key, merge_columns, mode_column_names, mode_of, shard_bounds)
+from karma_b200.kmer import KmerClustering
+from oracle import kmer_oracle as ko
+
+
+def test_reference_test_suite_passes_on_the_mirror():
+    # /root/reference/tests/test_kmer.py:6-8
+    assert KmerClustering.is_palindrome("ACGT") is False
+    assert KmerClustering.is_palindrome("AAAA") is True
+
+
+def test_mode_of_matches_reference_errors():
+    assert mode_of("5p6") == _lib.KB_MODE_5P6 and mode_of(4) == _lib.KB_MODE_K(4) and mode_of(7) == 23
+    with pytest.raises(TypeError):            # kmer.py:84 `len(sequence) - "4p5"`
+        mode_of("4p5")
+    with pytest.raises(_lib.KarmaB200Error):
+        mode_of(9)
+
+
+def test_column_names_match_oracle_order():
+    assert mode_column_names(_lib.KB_MODE_5P6) == ko.columns_5p6_full()
+    assert mode_column_names(_lib.KB_MODE_K(3)) == sorted(mode_column_names(_lib.KB_MODE_K(3)))
+    assert len(mode_column_names(_lib.KB_MODE_DENSE_5_6)) == 5120
+
+
+def _pack_key(s):
+    key = 0
+    for t, ch in enumerate(s):
+        key |= (ord(ch) + 1) << (9 * (6 - t))
+    return key
+
+
+def test_exotic_key_order_is_python_string_order():
+    words = ["ACGTN", "ACGTNA", "NACGT", "acgtA", "A\rCGT", "TTTTN", "ACGT\xff", "ACGTa", "ACGTNN", "\x00ACGT"]
+    keys = [_pack_key(w) for w in words]
+    assert [decode_exotic_key(k) for k in keys] == words
+    assert [words[i] for i in np.argsort(np.array(keys, dtype=np.uint64))] == sorted(words)
+
+
+def test_merge_columns_reproduces_sorted_union(golden):
+    case = next(c for c in golden if c["name"] == "KA1")
+    names = mode_column_names(_lib.KB_MODE_5P6)
+    acgt = [c for c in case["columns"] if set(c) <= set("ACGT")]
+    exo = [c for c in case["columns"] if not set(c) <= set("ACGT")]
+    present = np.array([n in set(acgt) for n in names])
+    cols, colmap, keycol = merge_columns(names, present, exo[::-1])
+    assert cols == case["columns"]
+    assert all(cols[colmap[i]] == names[i] for i in np.flatnonzero(present)) and (colmap[~present] == -1).all()
+    assert [cols[j] for j in keycol] == exo[::-1]
+
+
+def test_shard_bounds_cover_and_align():
+    for n, w in [(10, 3), (8, 2), (7, 8), (50000, 8), (1, 4)]:
+        seen = []
+        for r in range(w):
+            lo, hi, per = shard_bounds(n, w, r)
+            assert lo == min(r * per, n) and hi - lo <= per
+            seen += list(range(lo, hi))
+        assert seen == list(range(n))
+
+
+def test_mask_list_same_as_reference_semantics():
+    seqs = {">a x": "A", ">b": "C", ">c": "G", ">d": "T", ">e": "A"}
+    mask = np.array([1, -1, 0, 1, -1])
+    labeled, unlabeled = KmerClustering._KmerClustering__mask_list(seqs, mask)
+    # reference (kmer.py:30-44) written out
+    exp_l, exp_u = [], []
+    for i in set(mask):
+        pos = [list(seqs.keys())[c].lstrip(">") for c, k in enumerate(mask) if k == i]
+        (exp_u if i == -1 else exp_l).append(pos)
+    assert labeled == exp_l and unlabeled == exp_u
+
+
+def test_cluster_file_resume_and_header_fix(tmp_path):
+    out = str(tmp_path)
+    with open(os.path.join(out, "cluster.txt"), "w") as f:
+        f.write("u1 extra\tu2\n")
+        f.write("a\tb c\n")
+        f.write("d\n")
+    k = KmerClustering({}, out, "5p6", 1)
+    k.run(2, 10, 0, 42, 2)                       # kmer.py:275-277: skips profile/UMAP/HDBSCAN
+    assert k.unlabeled_cluster == [["u1", "u2"]] and k.clusters == [["a", "b"], ["d"]]
+    assert k.output_file == f"{out}/cluster.txt" and k.output_eval == f"{out}/eval.txt"
+
+
+def test_run_flow_with_stubbed_umap_hdbscan(tmp_path, monkeypatch):
+    """run() hands the GPU profile + kNN to UMAP (precomputed_knn) and HDBSCAN and writes
+    cluster.txt / eval.txt in the reference format; the GPU step itself is stubbed here."""
+    seen = {}
+
+    class UMAP:
+        def __init__(self, **kw):
+            seen["umap"] = kw
+
+        def fit_transform(self, x):
+            seen["x"] = x
+            return x[:, :2]
+
+    class HDBSCAN:
+        def __init__(self, **kw):
+            seen["hdb"] = kw
+
+        def fit(self, emb):
+            self.labels_ = np.array([0, 0, -1, 1])
+            self.probabilities_ = np.array([1.0, 0.5, 0.0, 1.0])
+            return self
+
+    monkeypatch.setitem(sys.modules, "umap", types.SimpleNamespace(UMAP=UMAP))
+    monkeypatch.setitem(sys.modules, "hdbscan", types.SimpleNamespace(HDBSCAN=HDBSCAN))
+    seqs = {">c0 len=5": "ACGTA", ">c1": "ACGTT", ">c2": "GGGGG", ">c3": "TTTTT"}
+    k = KmerClustering(seqs, str(tmp_path), "5p6", 2)
+
+    def fake_profile(n_neighbors=None):
+        k.knn_indices = np.zeros((4, n_neighbors), dtype=np.int32)
+        k.knn_dists = np.zeros((4, n_neighbors), dtype=np.float32)
+        return np.eye(4)
+    monkeypatch.setattr(k, "_KmerClustering__calc_kmer_profile", fake_profile)
+    k.run(neighbors=2, components=10, dist=0, r_state=42, min_cluster_size=2)
+    assert seen["umap"]["n_neighbors"] == 2 and seen["umap"]["random_state"] == 42
+    idx, dst, _ = seen["umap"]["precomputed_knn"]
+    assert idx.shape == (4, 2) and dst.dtype == np.float32
+    assert seen["hdb"] == {"min_cluster_size": 2}
+    assert k.unlabeled_cluster == [["c2"]] and sorted(k.clusters) == [["c0", "c1"], ["c3"]]
+    lines = open(k.output_file).read().split("\n")
+    assert lines[0] == "c2"
+    ev = open(k.output_eval).read().split("\n")
+    assert ev[0].split("\t") == ["kmer_size", "n_neighbors", "n_components", "min_dist", "random_state",
+                                 "min_cluster_size", "unlabeled", "no_groups", "mean_probability"]
+    assert ev[1].split("\t")[:7] == ["5p6", "2", "10", "0", "42", "2", "1"]
+
+
+def test_knn_oracle_exact_vs_fp64():
+    from oracle import knn_oracle
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 6, (40, 30)).astype(np.uint32)
+    counts[7] = counts[3]                                  # exact duplicate -> tie at distance 0
+    key_len = rng.integers(5, 30, 40).astype(np.int32)
+    key_len[7] = key_len[3]
+    prof = counts / key_len[:, None].astype(np.float64)
+    i_e, d_e = knn_oracle.knn_exact(counts, key_len, 5)
+    i_f, d_f = knn_oracle.knn_fp64(prof, 5)
+    assert (i_e[:, 0] == np.arange(40)).all() and (i_f[:, 0] == np.arange(40)).all()
+    rep = knn_oracle.check_knn(i_e, np.sqrt(d_e), knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+    assert i_e[3, 1] == 7 and i_e[7, 1] == 3 and d_e[3, 1] == 0.0
+    # a wrong answer must be caught
+    bad = i_f.copy()
+    bad[0, 1] = i_f[0, -1]
+    bad[0, -1] = (set(range(40)) - set(i_f[0].tolist())).pop()
+    rep = knn_oracle.check_knn(bad, np.sqrt(knn_oracle.d2_fp64(prof)[np.arange(40)[:, None], bad]), knn_oracle.d2_fp64(prof))
+    assert not knn_oracle.parity_ok(rep)
