@@ -178,11 +178,13 @@ KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
            int32_t* d_idx, float* d_dist, double* d_d2,
            void* d_workspace, int64_t workspace_bytes);
 
-/* Per-kernel device times (ms) of the most recent call of each stage, measured
- * with CUDA events on the context stream when timing is enabled.
+/* Per-stage device times.  With timing enabled every launch of a stage is bracketed
+ * by a CUDA-event pair on the context stream (a ring of 128 pairs per stage).
+ * kb_stage_ms synchronises, returns the mean duration (ms) and the number of launches
+ * recorded since the last read, and resets the stage.
  *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank */
 KB_API int kb_enable_timing(kb_ctx* ctx, int on);
-KB_API int kb_last_ms(kb_ctx* ctx, int which, float* ms);   /* synchronises */
+KB_API int kb_stage_ms(kb_ctx* ctx, int which, float* mean_ms, int* n_launches);
 /* Number of kernels this library launched since the context was created. */
 KB_API int64_t kb_launch_count(kb_ctx* ctx);
 

@@ -50,7 +50,7 @@ SIGNATURES = {
     "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int64, c_int64,
                        _P, _P, _P, _P, c_int64]),
     "kb_enable_timing": (c_int, [_P, c_int]),
-    "kb_last_ms": (c_int, [_P, c_int, POINTER(c_float)]),
+    "kb_stage_ms": (c_int, [_P, c_int, POINTER(c_float), POINTER(c_int)]),
     "kb_launch_count": (c_int64, [_P]),
 }
 

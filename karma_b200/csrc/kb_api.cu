@@ -66,10 +66,6 @@ extern "C" int kb_create(kb_ctx** out, int device) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->stream = 0;
-    for (int i = 0; i < KB_N_TIMERS; ++i) {
-        KB_CUDA(cudaEventCreate(&c->ev0[i]));
-        KB_CUDA(cudaEventCreate(&c->ev1[i]));
-    }
     *out = c;
     return KB_OK;
 }
@@ -83,7 +79,11 @@ static void kb_free_exotic(kb_ctx* c) {
 extern "C" int kb_destroy(kb_ctx* c) {
     if (!c) return KB_OK;
     cudaSetDevice(c->device);
-    for (int i = 0; i < KB_N_TIMERS; ++i) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
+    if (c->ev0) {
+        for (int i = 0; i < KB_N_TIMERS; ++i)
+            for (int j = 0; j < KB_EV_RING; ++j) { cudaEventDestroy(c->ev0[i][j]); cudaEventDestroy(c->ev1[i][j]); }
+        free(c->ev0); free(c->ev1);
+    }
     cudaFree(c->d_k1_scratch);
     kb_free_exotic(c);
     free(c);
@@ -98,15 +98,37 @@ extern "C" int kb_set_stream(kb_ctx* c, void* s) {
 
 extern "C" int kb_enable_timing(kb_ctx* c, int on) {
     KB_CHECK_ARG(c, "ctx");
+    if (on && !c->ev0) {
+        KB_CUDA(cudaSetDevice(c->device));
+        c->ev0 = (cudaEvent_t(*)[KB_EV_RING])calloc(KB_N_TIMERS, sizeof(*c->ev0));
+        c->ev1 = (cudaEvent_t(*)[KB_EV_RING])calloc(KB_N_TIMERS, sizeof(*c->ev1));
+        if (!c->ev0 || !c->ev1) { kb_set_error("out of host memory"); return KB_EINVAL; }
+        for (int i = 0; i < KB_N_TIMERS; ++i)
+            for (int j = 0; j < KB_EV_RING; ++j) {
+                KB_CUDA(cudaEventCreate(&c->ev0[i][j]));
+                KB_CUDA(cudaEventCreate(&c->ev1[i][j]));
+            }
+    }
     c->timing = on ? 1 : 0;
+    for (int i = 0; i < KB_N_TIMERS; ++i) c->ev_n[i] = 0;
     return KB_OK;
 }
 
-extern "C" int kb_last_ms(kb_ctx* c, int which, float* ms) {
-    KB_CHECK_ARG(c && ms && which >= 0 && which < KB_N_TIMERS, "which");
-    if (!c->ev_valid[which]) { kb_set_error("stage %d was not timed", which); return KB_EINVAL; }
-    KB_CUDA(cudaEventSynchronize(c->ev1[which]));
-    KB_CUDA(cudaEventElapsedTime(ms, c->ev0[which], c->ev1[which]));
+extern "C" int kb_stage_ms(kb_ctx* c, int which, float* mean_ms, int* n_launches) {
+    KB_CHECK_ARG(c && mean_ms && which >= 0 && which < KB_N_TIMERS, "which");
+    const int n = c->ev_n[which] < KB_EV_RING ? c->ev_n[which] : KB_EV_RING;
+    if (n_launches) *n_launches = n;
+    *mean_ms = 0.f;
+    if (!c->ev0 || n == 0) { kb_set_error("stage %d was not timed", which); return KB_EINVAL; }
+    double sum = 0.0;
+    for (int j = 0; j < n; ++j) {
+        float ms = 0.f;
+        KB_CUDA(cudaEventSynchronize(c->ev1[which][j]));
+        KB_CUDA(cudaEventElapsedTime(&ms, c->ev0[which][j], c->ev1[which][j]));
+        sum += ms;
+    }
+    *mean_ms = (float)(sum / n);
+    c->ev_n[which] = 0;
     return KB_OK;
 }
 

@@ -8,14 +8,18 @@
 #include "../../include/karma_b200.h"
 
 #define KB_N_TIMERS 8
+#define KB_EV_RING 128
 
 struct kb_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;
     int timing;
-    cudaEvent_t ev0[KB_N_TIMERS], ev1[KB_N_TIMERS];
-    int ev_valid[KB_N_TIMERS];
+    // per-stage ring of CUDA-event pairs recorded on the launching stream; read (and
+    // reset) by kb_stage_ms without synchronising inside the timed region
+    cudaEvent_t (*ev0)[KB_EV_RING];
+    cudaEvent_t (*ev1)[KB_EV_RING];
+    int ev_n[KB_N_TIMERS];          // launches recorded since the last reset
     int64_t launches;
     // K1 scratch: work counter + long-contig list
     int32_t* d_k1_scratch;          // [0] contig counter, [1] n_long, [2..] long ids
@@ -43,12 +47,12 @@ int kb_cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 struct KbTimer {
-    kb_ctx* c; int which;
-    KbTimer(kb_ctx* ctx, int w) : c(ctx), which(w) {
-        if (c->timing) cudaEventRecord(c->ev0[which], c->stream);
+    kb_ctx* c; int which; int slot;
+    KbTimer(kb_ctx* ctx, int w) : c(ctx), which(w), slot(0) {
+        if (c->timing) { slot = c->ev_n[which] % KB_EV_RING; cudaEventRecord(c->ev0[which][slot], c->stream); }
     }
     ~KbTimer() {
-        if (c->timing) { cudaEventRecord(c->ev1[which], c->stream); c->ev_valid[which] = 1; }
+        if (c->timing) { cudaEventRecord(c->ev1[which][slot], c->stream); c->ev_n[which]++; }
     }
 };
 

@@ -163,10 +163,11 @@ class Engine:
     def enable_timing(self, on=True):
         check(self.lib.kb_enable_timing(self.ctx, 1 if on else 0))
 
-    def last_ms(self, stage):
-        ms = c_float()
-        check(self.lib.kb_last_ms(self.ctx, _lib.STAGES[stage], byref(ms)))
-        return ms.value
+    def stage_ms(self, stage):
+        """(mean ms, launches) of a stage since the last read; synchronises."""
+        ms, n = c_float(), ctypes.c_int()
+        check(self.lib.kb_stage_ms(self.ctx, _lib.STAGES[stage], byref(ms), byref(n)))
+        return ms.value, n.value
 
     def launches(self):
         return int(self.lib.kb_launch_count(self.ctx))

@@ -1,0 +1,143 @@
+"""K1/K1x/K2/K3 parity on a B200: counts bit-exact against the oracle, the fp64 profile
+bit-exact against the golden vectors produced by the real kmer.py."""
+import numpy as np
+import pytest
+import torch
+
+from karma_b200 import _lib, synth
+from karma_b200.engine import mode_of
+from oracle import kmer_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+def _count(engine, bases, offsets, mode_name):
+    mode = mode_of(mode_name)
+    key_len = np.ones(len(offsets) - 1, dtype=np.int32)
+    d_bases, d_offsets, _ = engine.upload(bases, offsets, key_len)
+    counts, exotic, presence = engine.count(d_bases, d_offsets, len(offsets) - 1, mode)
+    torch.cuda.synchronize()
+    return (counts.cpu().numpy().view(np.uint32), exotic.cpu().numpy().view(np.uint32),
+            presence.cpu().numpy() != 0)
+
+
+@pytest.mark.parametrize("mode", ["5p6", "5+6", "4+5", 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("kind", ["S0", "S1"])
+def test_counts_bit_exact(engine, mode, kind):
+    asm = synth.make(kind, 257)
+    got, exotic, presence = _count(engine, asm.bases, asm.offsets, mode)
+    want, wexo = ko.counts_mode(asm.bases, asm.offsets, mode)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert np.array_equal(exotic, wexo.astype(np.uint32))
+    assert np.array_equal(presence, want.any(0))
+
+
+def _pack(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    return np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8), offsets
+
+
+@pytest.mark.parametrize("mode", ["5p6", "5+6", 4, 7])
+def test_counts_edge_cases(engine, mode):
+    rng = np.random.default_rng(5)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    seqs = ["", "A", "ACGT", "ACGTA", "ACGTAC", "ACGTACG", "A" * 700, "ACGT" * 50, rnd(15), rnd(16), rnd(17),
+            rnd(31), rnd(33), rnd(2047), rnd(2048), rnd(2049), rnd(4097), "", rnd(9), "CGTTGC" * 7, "GAGGAG",
+            "NNNNNNNNNN", "ACGTNACGTACGTTGCAACGTnACGT", rnd(100) + "N" + rnd(100), "acgtacgtacgt", rnd(5000)]
+    bases, offsets = _pack(seqs)
+    got, exotic, presence = _count(engine, bases, offsets, mode)
+    want, wexo = ko.counts_mode(bases, offsets, mode)
+    assert np.array_equal(got, want)
+    assert np.array_equal(exotic, wexo.astype(np.uint32))
+    assert np.array_equal(presence, want.any(0))
+
+
+@pytest.mark.parametrize("mode", ["5p6", "5+6", 7])
+def test_long_contig_split_path(engine, mode):
+    """Contigs above the 64 kb threshold are tiled over CTAs and merged."""
+    rng = np.random.default_rng(9)
+    lens = [300, 70000, 65536, 65537, 1200, 200001, 16385 * 4 + 3, 50]
+    seqs = ["".join("ACGT"[i] for i in rng.integers(0, 4, n)) for n in lens]
+    seqs[5] = seqs[5][:1000] + "N" + seqs[5][1001:150000] + "a" + seqs[5][150001:]
+    bases, offsets = _pack(seqs)
+    got, exotic, presence = _count(engine, bases, offsets, mode)
+    n_long, ex_total = engine.count_stats()
+    want, wexo = ko.counts_mode(bases, offsets, mode)
+    assert n_long == 4
+    assert np.array_equal(got, want)
+    assert np.array_equal(exotic, wexo.astype(np.uint32)) and ex_total == int(wexo.sum())
+    assert np.array_equal(presence, want.any(0))
+
+
+def test_profile_bit_exact_against_reference_golden(engine, golden):
+    """Through the reference-facing class: columns, float64 matrix and exit(1) behaviour
+    must equal what /root/reference/karma/kmer.py produced (tests/golden)."""
+    from karma_b200.kmer import KmerClustering
+    for c in golden:
+        seqs = dict(zip(c["keys"], c["seqs"]))
+        k = KmerClustering(seqs, "/tmp", c["kmer_size"], 2)
+        k._engine = engine
+        if "exit" in c:
+            with pytest.raises(SystemExit) as e:
+                k._KmerClustering__calc_kmer_profile()
+            assert e.value.code == c["exit"]
+            continue
+        mat = k._KmerClustering__calc_kmer_profile()
+        cols = sorted(k.kmers, key=k.kmers.get)
+        assert cols == c["columns"], c["name"]
+        assert mat.dtype == np.float64 and list(mat.shape) == c["shape"], c["name"]
+        assert np.ascontiguousarray(mat).tobytes().hex() == c["matrix_hex"], c["name"]
+
+
+@pytest.mark.parametrize("kmer_size", ["5p6", 4, 6])
+def test_profile_bit_exact_against_oracle_with_exotic_bytes(engine, kmer_size):
+    from karma_b200.kmer import KmerClustering
+    rng = np.random.default_rng(21)
+    seqs = {}
+    for i in range(40):
+        alpha = "ACGT" if i % 3 else "ACGTNacgtRY\r"
+        L = int(rng.integers(8, 600))
+        seqs[">c%d_%s" % (i, "x" * int(rng.integers(0, 20)))] = "".join(alpha[j] for j in rng.integers(0, len(alpha), L))
+    k = KmerClustering(seqs, "/tmp", kmer_size, 2)
+    k._engine = engine
+    mat = k._KmerClustering__calc_kmer_profile()
+    cols, want = ko.profile_np(seqs, kmer_size)
+    assert sorted(k.kmers, key=k.kmers.get) == cols
+    assert mat.tobytes() == want.tobytes()
+
+
+def test_full_size_properties_50k(engine):
+    """BASELINE config 2 size (50k contigs): size-independent properties of the count
+    matrix -- every row of the 5-mer block sums to L-4, the 6-mer block to L-5, a
+    checksum of checksums against numpy, and linearity (counts of a concatenated pair
+    differ from the sum of the parts only by the junction windows)."""
+    asm = synth.s1_families(50000)
+    L = np.diff(asm.offsets)
+    got, exotic, presence = _count(engine, asm.bases, asm.offsets, "5+6")
+    assert exotic.sum() == 0
+    assert np.array_equal(got[:, :1024].sum(1, dtype=np.int64), L - 4)
+    assert np.array_equal(got[:, 1024:].sum(1, dtype=np.int64), L - 5)
+    sub = np.arange(0, 50000, 97)
+    want, _ = ko.counts_mode(*_slice(asm, sub), "5+6")
+    assert np.array_equal(got[sub], want)
+    # marginalising the 6-mer block over its last base gives the 5-mer block minus the last window
+    marg = got[:, 1024:].reshape(50000, 1024, 4).sum(2)
+    diff = got[:, :1024].astype(np.int64) - marg
+    assert (diff >= 0).all() and np.array_equal(diff.sum(1), np.ones(50000, dtype=np.int64))
+    g5p6, _, _ = _count(engine, asm.bases, asm.offsets, "5p6")
+    full = ko.columns_5p6_full()
+    is5 = np.array([len(c) == 5 for c in full])
+    assert np.array_equal(g5p6[:, is5], got[:, :1024])
+
+
+def _slice(asm, rows):
+    seqs = [asm.bases[asm.offsets[r]:asm.offsets[r + 1]] for r in rows]
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    off = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return np.concatenate(seqs), off

@@ -1,0 +1,114 @@
+"""K4 (SIMT and tcgen05) + K5 parity against the fp64 / exact-rational kNN oracle."""
+import numpy as np
+import pytest
+import torch
+
+from karma_b200 import _lib, synth
+from karma_b200.engine import mode_of, profile_and_knn
+from oracle import kmer_oracle as ko
+from oracle import knn_oracle
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = {"simt": _lib.KB_KNN_SIMT, "tc": _lib.KB_KNN_TC}
+
+
+def _run(engine, asm, kmer_size, k, impl):
+    return profile_and_knn(engine, asm.bases, asm.offsets, asm.key_len, kmer_size, n_neighbors=k, impl=IMPLS[impl])
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("kind,n,k", [("S1", 700, 2), ("S1", 700, 15), ("S0", 300, 5), ("S2", 900, 15), ("S1", 130, 24)])
+def test_knn_parity_5p6(engine, impl, kind, n, k):
+    asm = synth.make(kind, n)
+    res = _run(engine, asm, "5p6", k, impl)
+    cols, prof = ko.profile_np(asm.as_dict(), "5p6")
+    assert res["columns"] == cols and res["profile"].tobytes() == prof.tobytes()
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("kmer_size", ["5+6", "4+5", 4, 7])
+def test_knn_parity_other_modes(engine, impl, kmer_size):
+    asm = synth.s1_families(400, seed=77)
+    res = _run(engine, asm, kmer_size, 6, impl)
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, kmer_size)
+    if isinstance(kmer_size, int):
+        counts = counts[:, counts.any(0)]             # kmer.py keeps observed columns only
+    prof = counts / asm.key_len[:, None].astype(np.float64)
+    assert res["profile"].tobytes() == prof.tobytes()
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+
+
+def test_knn_exact_rational_truth_under_ties(engine):
+    """Duplicates and equal distances: the result must satisfy the tie rule against the
+    exact-rational oracle, self first, distance 0 to exact duplicates."""
+    asm = synth.s2_redundant(160, seed=4)
+    res = _run(engine, asm, "5p6", 4, "tc")
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, "5p6")
+    i_e, d_e = knn_oracle.knn_exact(counts, asm.key_len, 4, rows=range(0, 160, 8))
+    rows = np.arange(0, 160, 8)
+    prof = counts / asm.key_len[:, None].astype(np.float64)
+    rep = knn_oracle.check_knn(res["knn_idx"][rows], res["knn_dist"][rows], knn_oracle.d2_fp64(prof, rows), rows=rows)
+    assert knn_oracle.parity_ok(rep), rep
+    assert np.allclose(np.sqrt(d_e), res["knn_dist"][rows], rtol=1e-6, atol=0)
+    assert (res["knn_idx"][:, 0] == np.arange(160)).all() and (res["knn_dist"][:, 0] == 0).all()
+
+
+def test_tc_equals_simt_candidates(engine):
+    """Same scores, same tie rule: both candidate kernels must lead to identical output."""
+    asm = synth.s1_families(1500, seed=13)
+    a = _run(engine, asm, "5p6", 15, "simt")
+    b = _run(engine, asm, "5p6", 15, "tc")
+    assert np.array_equal(a["knn_idx"], b["knn_idx"]) and np.array_equal(a["knn_dist"], b["knn_dist"])
+
+
+def test_tensor_core_gram_is_exact(engine):
+    """The design relies on the fp16 x fp16 -> fp32 tensor-core Gram of integer counts
+    being exact below 2^24 (SURVEY 7 'verify on hardware'): the fp32 scores must then be
+    bit-identical to the same formula evaluated from an int64 Gram on the CPU."""
+    asm = synth.s1_families(384, seed=21)
+    mode = mode_of("5p6")
+    d_bases, d_offsets, d_len = engine.upload(asm.bases, asm.offsets, asm.key_len)
+    counts, _, _ = engine.count(d_bases, d_offsets, asm.n, mode)
+    _, operand, sqnorm, rowflag = engine.normalise(counts, 1088, d_len, want_profile=False)
+    k = 24
+    idx, dist, d2 = engine.knn(operand, d_len, sqnorm, rowflag, k, impl=_lib.KB_KNN_TC, want_d2=True)
+    torch.cuda.synchronize()
+    c = counts.cpu().numpy().view(np.uint32).astype(np.int64)
+    gram = c @ c.T
+    l = asm.key_len.astype(np.float64)
+    num = np.diag(gram)[:, None] * (l[None, :] ** 2) + np.diag(gram)[None, :] * (l[:, None] ** 2) - 2 * gram * np.outer(l, l)
+    truth = num / np.outer(l, l) ** 2
+    rep = knn_oracle.check_knn(idx.cpu().numpy(), dist.cpu().numpy(), truth)
+    assert knn_oracle.parity_ok(rep), rep
+    got = d2.cpu().numpy()
+    assert np.array_equal(got, truth[np.arange(asm.n)[:, None], idx.cpu().numpy()]), "rerank is not exact"
+
+
+def test_query_shard_equals_full(engine):
+    """Multi-GPU layout on one GPU: a query-row shard against all keys gives the same rows."""
+    asm = synth.s1_families(1000, seed=31)
+    mode = mode_of("5p6")
+    d_bases, d_offsets, d_len = engine.upload(asm.bases, asm.offsets, asm.key_len)
+    counts, _, _ = engine.count(d_bases, d_offsets, asm.n, mode)
+    _, operand, sqnorm, rowflag = engine.normalise(counts, 1088, d_len, want_profile=False)
+    full_i, full_d, _ = engine.knn(operand, d_len, sqnorm, rowflag, 5, impl=_lib.KB_KNN_TC)
+    part_i, part_d, _ = engine.knn(operand, d_len, sqnorm, rowflag, 5, q_row0=250, nq=333, impl=_lib.KB_KNN_TC)
+    assert torch.equal(full_i[250:583], part_i) and torch.equal(full_d[250:583], part_d)
+
+
+def test_full_size_knn_properties_50k(engine):
+    """BASELINE config 2 (50k contigs, 5p6, n_neighbors=2) at full size: structural
+    properties for all rows and the tie-rule check on a row sample against fp64 brute force."""
+    asm = synth.s1_families(50000)
+    res = _run(engine, asm, "5p6", 2, "tc")
+    idx, dist = res["knn_idx"], res["knn_dist"]
+    assert idx.shape == (50000, 2) and (idx[:, 0] == np.arange(50000)).all() and (dist[:, 0] == 0).all()
+    assert (idx[:, 1] != idx[:, 0]).all() and (idx >= 0).all() and (idx < 50000).all() and np.isfinite(dist).all()
+    prof = res["profile"]
+    rows = np.arange(0, 50000, 1499)
+    rep = knn_oracle.check_knn(idx[rows], dist[rows], knn_oracle.d2_fp64(prof, rows), rows=rows)
+    assert knn_oracle.parity_ok(rep), rep
