@@ -32,7 +32,7 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, KbKnn
     p->off_colmeta = off; off += kb_round_up(p->nk_pad * (int64_t)sizeof(float2), 256);
     p->off_score = off;   off += kb_round_up(nq * p->splits * p->kp * (int64_t)sizeof(float), 256);
     p->off_idx = off;     off += kb_round_up(nq * p->splits * p->kp * (int64_t)sizeof(int32_t), 256);
-    p->off_counter = off; off += 256;
+    p->off_rowthr = off;  off += kb_round_up(nq * (int64_t)sizeof(int32_t), 256);
     p->total = off;
     return KB_OK;
 }
@@ -41,8 +41,10 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 k4_prep_colmeta(const int32_t* __restrict__ key_len, const double* __restrict__ sqnorm,
-                const uint8_t* __restrict__ rowflag, int64_t nk, int64_t nk_pad, float2* __restrict__ colmeta) {
+                const uint8_t* __restrict__ rowflag, int64_t nk, int64_t nk_pad, float2* __restrict__ colmeta,
+                int32_t* __restrict__ row_thr, int64_t nq) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nq) row_thr[j] = 0x7f800000;                      // +inf as an ordered-int key
     if (j >= nk_pad) return;
     float2 cm;
     if (j < nk && !(rowflag && (rowflag[j] & 3))) {
@@ -306,7 +308,8 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
     const __half* op = reinterpret_cast<const __half*>(d_operand);
 
     k4_prep_colmeta<<<(unsigned)((p.nk_pad + 255) / 256), 256, 0, ctx->stream>>>(
-        d_key_len, d_sqnorm, d_rowflag, nk, p.nk_pad, reinterpret_cast<float2*>(ws + p.off_colmeta));
+        d_key_len, d_sqnorm, d_rowflag, nk, p.nk_pad, reinterpret_cast<float2*>(ws + p.off_colmeta),
+        reinterpret_cast<int32_t*>(ws + p.off_rowthr), nq);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     {

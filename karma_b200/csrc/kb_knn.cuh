@@ -14,7 +14,7 @@ struct KbKnnPlan {
     int splits;          // S
     int64_t nk_pad;      // colmeta length (multiple of bn)
     // workspace offsets (bytes)
-    int64_t off_colmeta, off_score, off_idx, off_counter, total;
+    int64_t off_colmeta, off_score, off_idx, off_rowthr, total;
 };
 
 int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, KbKnnPlan* p);
@@ -35,13 +35,12 @@ struct KbRowList {
 #pragma unroll
         for (int e = 0; e < KP; ++e) { s[e * ROWS + r] = __int_as_float(0x7f800000); i[e * ROWS + r] = -1; }
     }
-    // replace the current worst (at pos) and rescan for the new worst.  Cold path
-    // (an element beats the running threshold): kept out of line so the hot
-    // compare loop stays small.
-    __device__ __noinline__ void insert(int r, float v, int32_t j, float& thr, int& pos) {
+    // replace the current worst (at pos) and rescan for the new worst (cold path: an
+    // element beat the running bound).  thr/pos stay in registers.
+    __device__ __forceinline__ void insert(int r, float v, int32_t j, float& thr, int& pos) {
         s[pos * ROWS + r] = v; i[pos * ROWS + r] = j;
         float m = s[r]; int mp = 0;
-#pragma unroll
+#pragma unroll 4
         for (int e = 1; e < KP; ++e) {
             const float x = s[e * ROWS + r];
             if (x > m) { m = x; mp = e; }

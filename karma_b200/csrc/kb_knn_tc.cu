@@ -122,7 +122,39 @@ struct TcParams {
     const int32_t* key_len;
     float* cand_score;
     int32_t* cand_idx;
+    int32_t* row_thr;                 // per query row: best known KP-th score (ordered-int key), shared by all units
 };
+
+// Work unit u -> (query block, tile sweep).  Units are ordered split-major so that the
+// CTAs running at the same time sweep the same key tiles (L2 reuse of B).  The split
+// that runs FIRST for a query block is the one holding its diagonal tile, and its sweep
+// starts at that tile: a contig's isoforms/duplicates sit next to it in the assembly,
+// so the running thresholds are near-final after one tile and (through row_thr) prune
+// every later unit of the same rows.
+struct Unit {
+    int64_t mb; int s; int64_t t_lo, cnt, shift;
+    __device__ __forceinline__ Unit(const TcParams& p, int64_t u) {
+        mb = u % p.m_blocks;
+        const int s_run = (int)(u / p.m_blocks);
+        const int64_t td = (p.q_row0 + mb * BM) / BN;                 // diagonal tile of this block
+        int sd = (int)((td * p.splits) / p.n_tiles);
+        while (sd + 1 < p.splits && (p.n_tiles * (sd + 1)) / p.splits <= td) ++sd;
+        while (sd > 0 && (p.n_tiles * sd) / p.splits > td) --sd;
+        s = (s_run + sd) % p.splits;
+        t_lo = (p.n_tiles * s) / p.splits;
+        cnt = (p.n_tiles * (s + 1)) / p.splits - t_lo;
+        shift = (s == sd) ? td - t_lo : 0;
+    }
+    __device__ __forceinline__ int64_t tile(int64_t i) const {
+        int64_t t = i + shift;
+        if (t >= cnt) t -= cnt;
+        return t_lo + t;
+    }
+};
+
+// order-preserving float <-> int key (atomicMin on signed ints)
+__device__ __forceinline__ int32_t f2key(float f) { const int32_t i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float key2f(int32_t k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 template <int KP, int STAGES>
 struct Smem {
@@ -177,11 +209,10 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int64_t mb = u % p.m_blocks; const int s = (int)(u / p.m_blocks);
-                const int64_t t_lo = p.n_tiles * s / p.splits, t_hi = p.n_tiles * (s + 1) / p.splits;
-                const int32_t arow = (int32_t)(p.q_row0 + mb * BM);
-                for (int64_t t = t_lo; t < t_hi; ++t) {
-                    const int32_t brow = (int32_t)(t * BN);
+                const Unit un(p, u);
+                const int32_t arow = (int32_t)(p.q_row0 + un.mb * BM);
+                for (int64_t i = 0; i < un.cnt; ++i) {
+                    const int32_t brow = (int32_t)(un.tile(i) * BN);
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
                         const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE_BYTES;
@@ -201,9 +232,8 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int s = (int)(u / p.m_blocks);
-                const int64_t t_lo = p.n_tiles * s / p.splits, t_hi = p.n_tiles * (s + 1) / p.splits;
-                for (int64_t t = t_lo; t < t_hi; ++t) {
+                const Unit un(p, u);
+                for (int64_t i = 0; i < un.cnt; ++i) {
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -233,21 +263,24 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int et = threadIdx.x - 64;                     // 0..127
         KbRowList<KP, BM> list{reinterpret_cast<float*>(smem + L::OFF_LIST_S),
                                reinterpret_cast<int32_t*>(smem + L::OFF_LIST_I)};
+        const float4* cm4 = reinterpret_cast<const float4*>(smem + L::OFF_COLMETA);
         float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
         int acc = 0; uint32_t acc_phase = 0;
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int64_t mb = u % p.m_blocks; const int s = (int)(u / p.m_blocks);
-            const int64_t t_lo = p.n_tiles * s / p.splits, t_hi = p.n_tiles * (s + 1) / p.splits;
-            const int64_t q = mb * BM + r;
-            const float li = (q < p.nq) ? (float)p.key_len[p.q_row0 + q] : 1.f;
+            const Unit un(p, u);
+            const int64_t q = un.mb * BM + r;
+            const bool live = q < p.nq;
+            const float li = live ? (float)p.key_len[p.q_row0 + q] : 1.f;
             list.init(r);
-            float thr = __int_as_float(0x7f800000); int pos = 0;
-            for (int64_t t = t_lo; t < t_hi; ++t) {
-                const int64_t n0 = t * BN;
-                // stage this tile's key metadata (all 128 epilogue threads)
+            float thr = __int_as_float(0x7f800000);          // min(own KP-th best, row_thr): the prune bound
+            float own = thr; int pos = 0;                    // own list's worst entry and its slot
+            for (int64_t i = 0; i < un.cnt; ++i) {
+                const int64_t n0 = un.tile(i) * BN;
+                // stage this tile's key metadata (all 128 epilogue threads); refresh the shared bound
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 cm_s[et] = p.colmeta[n0 + et];
                 cm_s[et + 128] = p.colmeta[n0 + et + 128];
+                if (live) thr = fminf(thr, key2f(__ldcg(p.row_thr + q)));
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bar_tfull + 8 * acc, acc_phase, 4);
                 tc_fence_after();
@@ -257,19 +290,40 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
+                    // hot path: branch-free scores + chunk minimum
+                    float sc[32];
+                    float m0 = thr, m1 = thr, m2 = thr, m3 = thr;
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) {
-                        const float sc = kb_score(__uint_as_float(v[x]), cm_s[c * 32 + x], li);
-                        if (sc < thr) list.insert(r, sc, (int32_t)(n0 + c * 32 + x), thr, pos);
+                    for (int x = 0; x < 32; x += 2) {
+                        const float4 cm = cm4[c * 16 + (x >> 1)];
+                        sc[x] = fmaf(__uint_as_float(v[x]), cm.x, li * cm.y);
+                        sc[x + 1] = fmaf(__uint_as_float(v[x + 1]), cm.z, li * cm.w);
+                    }
+#pragma unroll
+                    for (int x = 0; x < 32; x += 4) {
+                        m0 = fminf(m0, sc[x]); m1 = fminf(m1, sc[x + 1]);
+                        m2 = fminf(m2, sc[x + 2]); m3 = fminf(m3, sc[x + 3]);
+                    }
+                    if (fminf(fminf(m0, m1), fminf(m2, m3)) < thr) {
+                        // cold path: some element of this chunk beats the bound
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            if (sc[x] < thr) {
+                                list.insert(r, sc[x], (int32_t)(n0 + c * 32 + x), own, pos);
+                                thr = fminf(thr, own);
+                            }
+                        }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                // publish a full list's bound for the other units of these rows
+                if (live && own < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(own));
             }
-            if (q < p.nq) {
-                const int64_t base = (q * p.splits + s) * KP;
+            if (live) {
+                const int64_t base = (q * p.splits + un.s) * KP;
 #pragma unroll
                 for (int e = 0; e < KP; ++e) {
                     p.cand_score[base + e] = list.s[e * BM + r];
@@ -332,6 +386,7 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
     prm.key_len = d_key_len;
     prm.cand_score = reinterpret_cast<float*>(ws + p.off_score);
     prm.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
+    prm.row_thr = reinterpret_cast<int32_t*>(ws + p.off_rowthr);
     const int64_t n_units = p.m_blocks * p.splits;
     switch (p.kp) {
         case 8: return launch_tc<8, 4>(ctx, tmap, prm, n_units);

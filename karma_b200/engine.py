@@ -172,6 +172,24 @@ class Engine:
     def launches(self):
         return int(self.lib.kb_launch_count(self.ctx))
 
+    # ---- host-side plumbing -------------------------------------------------------
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def host_buffer(self, name, shape, dtype, reuse):
+        """Pinned host tensor for a result.  ``reuse``: one buffer per name, kept by the
+        engine and overwritten by the next call."""
+        if not reuse:
+            return torch.empty(shape, dtype=dtype, pin_memory=True)
+        cache = self.__dict__.setdefault("_host", {})
+        t = cache.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            cache[name] = t
+        return t
+
     # ---- uploads ---------------------------------------------------------------
     def upload(self, bases, offsets, key_len, pinned=False):
         """Host arrays -> device tensors.  ``bases`` is padded so that the kernel's
@@ -298,13 +316,19 @@ class Engine:
 # ---------------------------------------------------------------------------------------
 
 def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbors=None,
-                    impl=KB_KNN_AUTO, want_profile=True, group=None, rank=0, world=1, row0=0, n_total=None):
+                    impl=KB_KNN_AUTO, want_profile=True, group=None, rank=0, world=1, row0=0, n_total=None,
+                    reuse_host=False):
     """Run the hot path on host buffers.
 
     bases/offsets/key_len describe THIS rank's contigs (all of them when world==1).
     Returns dict(columns, profile (n,D') float64 ndarray or None, knn_idx, knn_dist)
     where the kNN rows are this rank's contigs against ALL contigs (global indices).
     Raises ZeroRowError when a contig is shorter than k (kmer.py:250-258).
+
+    The float64 profile (the largest transfer of the path: 8*D' bytes per contig) goes
+    back to pinned host memory on a side stream while the kNN kernels run.  With
+    ``reuse_host`` the pinned result buffers are owned by the engine and overwritten
+    by the next call (a serving loop); otherwise every call returns fresh arrays.
     """
     mode = mode_of(kmer_size)
     n = len(offsets) - 1
@@ -326,14 +350,28 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
         counts = counts.contiguous()
     profile, operand, sqnorm, rowflag = engine.normalise(counts, d_cols, d_key_len, want_profile=want_profile,
                                                          want_operand=n_neighbors is not None)
+    main = torch.cuda.current_stream(engine.device)
+    h_profile = None
+    if want_profile:
+        # D2H of the profile overlaps the kNN: side stream ordered after K3
+        h_profile = engine.host_buffer("profile", (n, d_cols), torch.float64, reuse_host)
+        side = engine.side_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            h_profile.copy_(profile, non_blocking=True)
+        profile.record_stream(side)
     flags = rowflag.cpu().numpy()
     zero = np.flatnonzero(flags & 4)
     if len(zero):
+        torch.cuda.synchronize(engine.device)
         raise ZeroRowError(int(zero[0]) + row0)
     out = {"columns": columns, "profile": None, "knn_idx": None, "knn_dist": None,
            "d_profile": profile, "d_operand": operand}
     if n_neighbors is not None:
         if (flags & 3).any():
+            torch.cuda.synchronize(engine.device)
             raise _lib.KarmaB200Error(-6, "a k-mer count > 2048 or a squared norm >= 2^24 needs the exact side path (not built yet)")
         if group is not None and world > 1:
             # the one exchange step: every rank needs all keys (operand + row metadata);
@@ -346,8 +384,14 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
             idx, dst, _ = engine.knn(all_op, all_len, all_sq, all_fl, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
         else:
             idx, dst, _ = engine.knn(operand, d_key_len, sqnorm, rowflag, n_neighbors, impl=impl)
-        out["knn_idx"] = idx.cpu().numpy()
-        out["knn_dist"] = dst.cpu().numpy()
+        h_idx = engine.host_buffer("knn_idx", tuple(idx.shape), torch.int32, reuse_host)
+        h_dst = engine.host_buffer("knn_dist", tuple(dst.shape), torch.float32, reuse_host)
+        h_idx.copy_(idx, non_blocking=True)
+        h_dst.copy_(dst, non_blocking=True)
+        main.synchronize()
+        out["knn_idx"] = h_idx.numpy()
+        out["knn_dist"] = h_dst.numpy()
     if want_profile:
-        out["profile"] = profile.cpu().numpy()
+        engine.side_stream().synchronize()
+        out["profile"] = h_profile.numpy()
     return out
