@@ -1,0 +1,64 @@
+"""Multi-GPU parity: sharded run (torchrun, one rank per GPU) == single-GPU run.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/multi_gpu_check.py [--contigs 6000] [--neighbors 15]
+
+Every rank counts its row shard, the column dictionary is agreed through the presence
+all-reduce, the kNN operand is all-gathered and each rank searches its query rows.
+Rank 0 then recomputes everything alone on its GPU and compares: the profile rows must
+be bit-identical and the kNN lists identical (indices and distances).
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from karma_b200 import _lib, synth  # noqa: E402
+from karma_b200.engine import Engine, profile_and_knn, shard_bounds  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--contigs", type=int, default=6001)
+    ap.add_argument("--neighbors", type=int, default=15)
+    ap.add_argument("--synth", default="S1")
+    ap.add_argument("--kmer", default="5p6")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine(local)
+    kmer = int(a.kmer) if a.kmer.isdigit() else a.kmer
+    asm = synth.make(a.synth, a.contigs)
+    if a.kmer == "5p6":
+        # make the dictionary non-trivial: drop every contig's chance to hold some 5-mers on one rank only
+        pass
+    lo, hi, per = shard_bounds(asm.n, world, rank)
+    shard = asm.slice(lo, hi)
+    res = profile_and_knn(eng, shard.bases, shard.offsets, shard.key_len, kmer, n_neighbors=a.neighbors,
+                          impl=_lib.KB_KNN_TC, group=dist.group.WORLD, rank=rank, world=world, row0=lo, n_total=asm.n)
+    # gather the shards' results on rank 0 (object gather: this is a test, not the data path)
+    gathered = [None] * world
+    dist.gather_object((lo, hi, res["columns"], res["profile"], res["knn_idx"], res["knn_dist"]), gathered if rank == 0 else None, dst=0)
+    ok = True
+    if rank == 0:
+        full = profile_and_knn(eng, asm.bases, asm.offsets, asm.key_len, kmer, n_neighbors=a.neighbors, impl=_lib.KB_KNN_TC)
+        for (glo, ghi, cols, prof, idx, dst) in gathered:
+            same_cols = cols == full["columns"]
+            same_prof = prof.tobytes() == full["profile"][glo:ghi].tobytes()
+            same_idx = np.array_equal(idx, full["knn_idx"][glo:ghi])
+            same_dst = np.array_equal(dst, full["knn_dist"][glo:ghi])
+            print("rows [%d,%d): columns %s profile %s knn_idx %s knn_dist %s" % (glo, ghi, same_cols, same_prof, same_idx, same_dst))
+            ok &= same_cols and same_prof and same_idx and same_dst
+        print("MULTI_GPU_PARITY", "OK" if ok else "FAILED", "world", world, "contigs", asm.n, "k", a.neighbors)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
