@@ -224,7 +224,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     from karma_b200 import _lib, synth
-    from karma_b200.engine import (Engine, all_gather_padded, mode_of, profile_and_knn, shard_bounds)
+    from karma_b200.engine import Engine, device_pass, mode_of, profile_and_knn, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -260,32 +260,16 @@ def run_ours(a):
     cols_full = eng.lib.kb_mode_columns(mode)
     b_counts = torch.empty((n, cols_full), dtype=torch.int32, device=eng.device)
     b_exotic = torch.empty(n, dtype=torch.int32, device=eng.device)
-    b_presence = torch.empty(cols_full, dtype=torch.int32, device=eng.device)
-    faithful = mode == _lib.KB_MODE_5P6 or mode >= 16
+    b_presence = torch.empty(cols_full + 1, dtype=torch.int32, device=eng.device)
     state = {}
 
+    bufs = {"counts": b_counts, "exotic": b_exotic, "presence": b_presence}
+
     def device_step():
-        counts, exotic, presence = eng.count(d_bases, d_offsets, n, mode, b_counts, b_exotic, b_presence)
-        if faithful:
-            _, ex_total = eng.count_stats()
-            columns, counts = eng.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence, ex_total, group=group)
-            d_cols = len(columns)
-        else:
-            d_cols = cols_full
-        profile, operand, sqnorm, rowflag = eng.normalise(counts, d_cols, d_keylen)
-        if world > 1:
-            all_op = all_gather_padded(operand, n, per, group, 0)
-            all_len = all_gather_padded(d_keylen, n, per, group, 1)
-            all_sq = all_gather_padded(sqnorm, n, per, group, 0)
-            all_fl = all_gather_padded(rowflag, n, per, group, 3)
-            idx, dst, _ = eng.knn(all_op, all_len, all_sq, all_fl, k, q_row0=rank * per, nq=n, impl=impl)
-            g_idx = all_gather_padded(idx, n, per, group, -1)
-            g_dst = all_gather_padded(dst, n, per, group, 0)
-            state.update(idx=g_idx, dist=g_dst)
-        else:
-            idx, dst, _ = eng.knn(operand, d_keylen, sqnorm, rowflag, k, impl=impl)
-            state.update(idx=idx, dist=dst)
-        state.update(profile=profile, d_cols=d_cols)
+        r = device_pass(eng, d_bases, d_offsets, d_keylen, n, kmer_size, n_neighbors=k, impl=impl, want_profile=True,
+                        group=group, rank=rank, world=world, n_total=n_total, gather_lists=True, bufs=bufs)
+        state.update(idx=r.get("all_idx", r["idx"]), dist=r.get("all_dist", r["dist"]), profile=r["profile"],
+                     d_cols=r["d_cols"])
 
     def barrier():
         if world > 1:

@@ -92,10 +92,11 @@ KB_API int kb_set_stream(kb_ctx* ctx, void* cuda_stream);
  *                           byte other than A/C/G/T.  kmer.py gives such windows
  *                           their own string-keyed columns; they are NOT counted
  *                           in d_counts (see kb_exotic_*).
- *  d_presence uint32[D]     out (nullable): non-zero iff the column is non-zero
+ *  d_presence uint32[D+1]   out (nullable): [c] non-zero iff column c is non-zero
  *                           in some row (kmer.py:146-179 "observed k-mers");
- *                           must be zeroed by the caller (accumulates, so a
- *                           multi-call / multi-rank OR is possible).
+ *                           [D] non-zero iff some window holds a non-ACGT byte.
+ *                           Must be zeroed by the caller (accumulates, so a
+ *                           multi-call / multi-rank OR/MAX is possible).
  * Contigs longer than an internal threshold are split across CTAs and merged.
  */
 KB_API int kb_count(kb_ctx* ctx, int mode,

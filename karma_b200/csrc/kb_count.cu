@@ -29,16 +29,30 @@
 
 namespace {
 
-// 4 ASCII bytes -> (8 bits of 2-bit codes, first byte most significant; 4 bad bits)
-__device__ __forceinline__ void convert4(uint32_t w, uint32_t& code8, uint32_t& bad4) {
-    const uint32_t mA = __vcmpeq4(w, 0x41414141u);
-    const uint32_t mC = __vcmpeq4(w, 0x43434343u);
-    const uint32_t mG = __vcmpeq4(w, 0x47474747u);
-    const uint32_t mT = __vcmpeq4(w, 0x54545454u);
-    const uint32_t cb = (mC & 0x01010101u) | (mG & 0x02020202u) | (mT & 0x03030303u);
-    const uint32_t bb = ~(mA | mC | mG | mT) & 0x01010101u;
-    code8 = (cb * 0x40100401u) >> 24;          // c0<<6 | c1<<4 | c2<<2 | c3
-    bad4 = ((bb * 0x08040201u) >> 24) & 0xFu;  // b0<<3 | b1<<2 | b2<<1 | b3
+constexpr unsigned FULL = 0xffffffffu;
+
+// 4 ASCII bytes -> 8 bits of 2-bit codes (first byte most significant).  `xinv` gets a
+// non-zero byte wherever the input byte is not one of A/C/G/T.
+//   code = ((b>>1) ^ (b>>2)) & 3   maps A,C,G,T -> 0,1,2,3 (and garbage for other bytes),
+//   PRMT looks the code up in "ACGT" and the XOR with the input exposes every other byte.
+__device__ __forceinline__ uint32_t codes4(uint32_t w, uint32_t& xinv) {
+    const uint32_t t = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+    const uint32_t sel = (t & 0x3u) | ((t >> 4) & 0x30u) | ((t >> 8) & 0x300u) | ((t >> 12) & 0x3000u);
+    xinv = __byte_perm(0x54474341u, 0u, sel) ^ w;
+    return (t * 0x40100401u) >> 24;                            // c0<<6 | c1<<4 | c2<<2 | c3
+}
+// per-byte "non-zero" -> 4 bits, first byte most significant
+__device__ __forceinline__ uint32_t badbits4(uint32_t x) {
+    const uint32_t y = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    return (((y >> 7) * 0x08040201u) >> 24) & 0xFu;
+}
+
+// Branch-free conditional increment: windows that must not count are steered to a
+// per-thread dummy word behind the histogram (ptxas turns a predicated ATOMS into a
+// branch; a select + unconditional reduction is shorter and never diverges).
+__device__ __forceinline__ void red_shared_inc_if(uint32_t saddr, uint32_t dummy, uint32_t pred) {
+    const uint32_t a = pred ? saddr : dummy;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
 }
 
 template <int KA, int KB, bool PALB>
@@ -48,100 +62,205 @@ struct Bins {
     static constexpr int TOTAL = A + B;
 };
 
-// Accumulate windows starting in [lo, hi) of the contig at absolute byte `beg`
-// (length L) into the shared histogram.  Returns this thread's exotic-window tally.
-template <int KA, int KB, bool PALB, int THREADS>
-__device__ __forceinline__ uint32_t accumulate_range(const uint8_t* __restrict__ bases,
-                                                     int64_t beg, int64_t L, int64_t lo, int64_t hi,
-                                                     uint32_t* hist) {
+// Warp-cooperative accumulation of the windows starting in [lo, hi) of the contig at
+// absolute byte `beg` (length L) into `hist`.  The warp walks 512-byte spans starting
+// at the 16-byte aligned absolute address A_first, stepping A_stride; lane l owns the
+// 16 window starts of bytes [A0+16l, A0+16l+16) and needs 8 halo bytes, which are the
+// next lane's first bases (one shuffle; lane 31 loads its own).  Returns the lane's
+// tally of windows that contain a non-ACGT byte.
+template <int KA, int KB, bool PALB>
+__device__ __forceinline__ uint32_t accumulate_warp(const uint8_t* __restrict__ bases, int64_t beg, int64_t L,
+                                                    int64_t lo, int64_t hi, uint32_t* hist, uint32_t* dummy,
+                                                    int64_t A_first, int64_t A_stride, int lane) {
     constexpr int KMAX = (KB > KA) ? KB : KA;
-    static_assert(KMAX <= 8, "halo of one 64-bit load covers k <= 8 only");
-    constexpr int BINS_A = Bins<KA, KB, PALB>::A;
+    static_assert(KMAX <= 8, "8 halo bases cover k <= 8 only");
+    constexpr uint32_t BINS_A = Bins<KA, KB, PALB>::A;
     uint32_t exotic = 0;
     const int64_t end_abs = beg + L;
-    const int64_t a0 = (beg + lo) & ~int64_t(15);              // absolute, 16 B aligned
-    for (int64_t A = a0 + 16 * (int64_t)threadIdx.x; A < beg + hi; A += 16 * THREADS) {
-        // ---- load 24 bytes: positions A .. A+23 (absolute)
+    const uint32_t h32 = (uint32_t)__cvta_generic_to_shared(hist);
+    const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dummy);
+    for (int64_t A0 = A_first; A0 < beg + hi; A0 += A_stride) {          // warp-uniform trip count
+        const int64_t A = A0 + 16 * lane;
         uint4 v = make_uint4(0, 0, 0, 0);
-        uint2 h = make_uint2(0, 0);
         if (A < end_abs) v = __ldg(reinterpret_cast<const uint4*>(bases + A));
-        if (A + 16 < end_abs) h = __ldg(reinterpret_cast<const uint2*>(bases + A + 16));
-        uint32_t c0, c1, c2, c3, c4, c5, b0, b1, b2, b3, b4, b5;
-        convert4(v.x, c0, b0); convert4(v.y, c1, b1); convert4(v.z, c2, b2);
-        convert4(v.w, c3, b3); convert4(h.x, c4, b4); convert4(h.y, c5, b5);
-        // 24 bases, base j at bits [2*(23-j), 2*(23-j)+2); bad bit of base j at bit 23-j
-        const uint64_t codes = ((uint64_t)((c0 << 8) | c1) << 32) | (uint64_t)((c2 << 24) | (c3 << 16) | (c4 << 8) | c5);
-        const uint32_t bad = (b0 << 20) | (b1 << 16) | (b2 << 12) | (b3 << 8) | (b4 << 4) | b5;
-        const int64_t s0 = A - beg;                            // contig position of base 0 (may be < 0)
-        // window-start index range [wlo, whi) within this thread's 16
+        uint2 h = make_uint2(0, 0);
+        if (A + 16 < end_abs) h = __ldg(reinterpret_cast<const uint2*>(bases + A + 16));   // halo: L1 hit (next lane's vector)
+        uint32_t x0, x1, x2, x3, y0, y1;
+        const uint32_t own = (codes4(v.x, x0) << 24) | (codes4(v.y, x1) << 16) | (codes4(v.z, x2) << 8) | codes4(v.w, x3);
+        const uint32_t halo = (codes4(h.x, y0) << 8) | codes4(h.y, y1);
+        // 24 bases: base j at bits [2*(23-j), 2*(23-j)+2)
+        const uint64_t codes = ((uint64_t)own << 16) | (uint64_t)halo;
+        // non-ACGT bytes are rare: the per-base bad mask is only built when some lane saw one
+        uint32_t bad = 0;                                                // base j at bit 23-j
+        if (__any_sync(FULL, ((x0 | x1 | x2 | x3 | y0 | y1) != 0) && A < end_abs)) {
+            bad = (badbits4(x0) << 20) | (badbits4(x1) << 16) | (badbits4(x2) << 12) | (badbits4(x3) << 8) |
+                  (badbits4(y0) << 4) | badbits4(y1);
+        }
+        const int64_t s0 = A - beg;                                      // contig position of base 0 (may be < 0)
         const int64_t wlo64 = lo - s0;
-        const int wlo = wlo64 > 0 ? (int)(wlo64 < 16 ? wlo64 : 16) : 0;
+        const int wlo = wlo64 > 0 ? (wlo64 < 16 ? (int)wlo64 : 16) : 0;
+        // ---- component A: window w <-> bit 23-w
         const int64_t whiA64 = ((hi < L - KA + 1) ? hi : (L - KA + 1)) - s0;
         const int whiA = whiA64 < 0 ? 0 : (whiA64 < 16 ? (int)whiA64 : 16);
+        const uint32_t rA = whiA > wlo ? (1u << (24 - wlo)) - (1u << (24 - whiA)) : 0u;
+        uint32_t BA = bad;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) {
-            if (w >= wlo && w < whiA) {
-                const uint32_t code = (uint32_t)(codes >> (2 * (24 - KA - w))) & (BINS_A - 1);
-                const uint32_t bw = (bad >> (24 - KA - w)) & ((1u << KA) - 1);
-                if (bw == 0) atomicAdd(&hist[code], 1u);
-                else ++exotic;
-            }
-        }
+        for (int s = 1; s < KA; ++s) BA |= bad << s;
+        const uint32_t okA = rA & ~BA;
+        exotic += __popc(rA & BA);
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+            red_shared_inc_if(h32 + 4u * ((uint32_t)(codes >> (2 * (24 - KA - w))) & (BINS_A - 1)), d32, okA & (1u << (23 - w)));
         if constexpr (KB > 0) {
             const int64_t whiB64 = ((hi < L - KB + 1) ? hi : (L - KB + 1)) - s0;
             const int whiB = whiB64 < 0 ? 0 : (whiB64 < 16 ? (int)whiB64 : 16);
+            const uint32_t rB = whiB > wlo ? (1u << (24 - wlo)) - (1u << (24 - whiB)) : 0u;
+            uint32_t BB = bad;
 #pragma unroll
-            for (int w = 0; w < 16; ++w) {
-                if (w >= wlo && w < whiB) {
-                    const uint32_t code = (uint32_t)(codes >> (2 * (24 - KB - w))) & ((1u << (2 * KB)) - 1);
-                    const uint32_t bw = (bad >> (24 - KB - w)) & ((1u << KB) - 1);
-                    if (bw != 0) { ++exotic; continue; }
-                    if constexpr (PALB) {
-                        // string palindrome x1x2x3x3x2x1 (kmer.py:46-54): compare digit-reversed halves
-                        static_assert(!PALB || KB == 6, "palindromic component implemented for 6-mers");
-                        const uint32_t hi6 = code >> 6, lo6 = code & 63u;
-                        const uint32_t rev = ((lo6 & 3u) << 4) | (lo6 & 12u) | (lo6 >> 4);
-                        if (rev == hi6) atomicAdd(&hist[BINS_A + hi6], 1u);
-                    } else {
-                        atomicAdd(&hist[BINS_A + code], 1u);
-                    }
+            for (int s = 1; s < KB; ++s) BB |= bad << s;
+            const uint32_t okB = rB & ~BB;
+            exotic += __popc(rB & BB);
+            if constexpr (PALB) {
+                // string palindrome x1x2x3x3x2x1 (kmer.py:46-54), all 16 windows at once:
+                // field j of X_d is zero iff base j == base j+d; window w is a palindrome iff
+                // base w==w+5, w+1==w+4, w+2==w+3.  Result: bit 2*(23-w) set <=> NOT a palindrome.
+                static_assert(!PALB || KB == 6, "palindromic component implemented for 6-mers");
+                const uint64_t X5 = codes ^ (codes << 10), X3 = codes ^ (codes << 6), X1 = codes ^ (codes << 2);
+                const uint64_t np = (X5 | (X5 >> 1)) | ((X3 | (X3 >> 1)) << 2) | ((X1 | (X1 >> 1)) << 4);
+                // spread the valid-window bits (bit 23-w) to the 2-bit layout (bit 2*(23-w))
+                uint32_t sp = okB >> 8;                                  // window w at bit 15-w
+                sp = (sp | (sp << 8)) & 0x00FF00FFu; sp = (sp | (sp << 4)) & 0x0F0F0F0Fu;
+                sp = (sp | (sp << 2)) & 0x33333333u; sp = (sp | (sp << 1)) & 0x55555555u;
+                uint64_t pm = ~np & ((uint64_t)sp << 16);               // valid palindromic windows (~1/64 of all)
+                while (__any_sync(FULL, pm != 0)) {                     // warp-uniform trip count: no divergence
+                    const int b = pm ? 63 - __clzll((long long)pm) : 4;
+                    red_shared_inc_if(h32 + 4u * (BINS_A + ((uint32_t)(codes >> (b - 4)) & 63u)), d32, pm != 0);
+                    pm &= ~(1ull << b);
                 }
+            } else {
+#pragma unroll
+                for (int w = 0; w < 16; ++w)
+                    red_shared_inc_if(h32 + 4u * (BINS_A + ((uint32_t)(codes >> (2 * (24 - KB - w))) & ((1u << (2 * KB)) - 1))),
+                                      d32, okB & (1u << (23 - w)));
             }
         }
     }
     return exotic;
 }
 
-__device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* s_red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) s_red[warp] = v;
-    __syncthreads();
-    uint32_t t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
-    return t;
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Flush one histogram (group of NT threads, this thread = tid) to a count row with 128-bit
+// stores, clear it, and collect presence bits (bit 4*it+j for vector tid+it*NT, element j).
+template <int COLS, bool PERMUTE, int NT>
+__device__ __forceinline__ void flush_row(uint32_t* hist, uint32_t* __restrict__ row_out,
+                                          const uint16_t* __restrict__ perm, int tid, uint64_t& pres) {
+    constexpr int VEC = COLS / 4;
+    constexpr int ITERS = (VEC + NT - 1) / NT;
+    static_assert(COLS % 4 == 0, "row flush is 128-bit");
+    static_assert(ITERS * 4 <= 64, "presence bits live in one 64-bit register");
+    uint4* out = reinterpret_cast<uint4*>(row_out);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * NT;
+        if (i < VEC) {
+            uint4 r;
+            if constexpr (PERMUTE) {
+                const ushort4 p = *reinterpret_cast<const ushort4*>(perm + 4 * i);
+                r = make_uint4(hist[p.x], hist[p.y], hist[p.z], hist[p.w]);
+                hist[p.x] = 0; hist[p.y] = 0; hist[p.z] = 0; hist[p.w] = 0;
+            } else {
+                r = *reinterpret_cast<uint4*>(hist + 4 * i);
+                *reinterpret_cast<uint4*>(hist + 4 * i) = make_uint4(0, 0, 0, 0);
+            }
+            __stcs(out + i, r);                                          // streaming: the row is not re-read here
+            pres |= (uint64_t)((r.x != 0) | ((r.y != 0) << 1) | ((r.z != 0) << 2) | ((r.w != 0) << 3)) << (4 * it);
+        }
+    }
+}
+
+template <int COLS, int NT>
+__device__ __forceinline__ void publish_presence(uint32_t* __restrict__ presence, int tid, uint64_t pres) {
+    constexpr int VEC = COLS / 4;
+    constexpr int ITERS = (VEC + NT - 1) / NT;
+    if (!presence) return;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * NT;
+        if (i < VEC) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((pres >> (4 * it + j)) & 1) presence[4 * i + j] = 1u;
+        }
+    }
 }
 
 // scratch[0] = next contig, scratch[1] = number of long contigs, scratch[2..3] = exotic total (u64),
 // scratch[4..] = rows of the long contigs
+
+// ---- one WARP per contig (histogram <= 8 KB): no block barriers, 8 independent warps per CTA
+template <int KA, int KB, bool PALB, bool PERMUTE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
+              uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
+              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
+    constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
+    extern __shared__ __align__(16) uint32_t smem_hist[];
+    const int lane = threadIdx.x & 31;
+    uint32_t* hist = smem_hist + (threadIdx.x >> 5) * (COLS + 32);   // + one dummy word per lane
+    for (int i = lane; i < COLS; i += 32) hist[i] = 0;
+    __syncwarp();
+    uint64_t pres = 0;
+    while (true) {
+        int64_t row = 0;
+        if (lane == 0) row = (int64_t)atomicAdd(&scratch[0], 1);
+        row = __shfl_sync(FULL, row, 0);
+        if (row >= n) break;
+        const int64_t beg = offsets[row];
+        const int64_t L = offsets[row + 1] - beg;
+        uint32_t* out = counts + row * ld;
+        if (L > KB_LONG_THRESHOLD) {
+            // queue for the split kernel; zero the row it will red.add into
+            if (lane == 0) {
+                const int slot = atomicAdd(&scratch[1], 1);
+                scratch[4 + slot] = (int32_t)row;
+                if (exotic_out) exotic_out[row] = 0;
+            }
+            for (int i = lane; i < COLS / 4; i += 32) reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        const uint32_t ex = accumulate_warp<KA, KB, PALB>(bases, beg, L, 0, L, hist, hist + COLS + lane, beg & ~int64_t(15), 512, lane);
+        const uint32_t ex_total = warp_sum(ex);
+        if (lane == 0) {
+            if (exotic_out) exotic_out[row] = ex_total;
+            if (ex_total) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(scratch + 2), (unsigned long long)ex_total);
+                if (presence) presence[COLS] = 1u;               // "some window holds a non-ACGT byte"
+            }
+        }
+        __syncwarp();
+        flush_row<COLS, PERMUTE, 32>(hist, out, perm, lane, pres);
+        __syncwarp();
+    }
+    publish_presence<COLS, 32>(presence, lane, pres);
+}
+
+// ---- one CTA per contig (histograms of 16-64 KB)
 template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k1_count(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
-         uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-         uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
+k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
+             uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
+             uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
-    constexpr int VEC = (COLS + 3) / 4;                       // uint4 per row (COLS % 4 == 0)
-    constexpr int ITERS = (VEC + THREADS - 1) / THREADS;
-    static_assert(COLS % 4 == 0, "row flush is 128-bit");
-    static_assert(ITERS * 4 <= 64, "presence bits live in one 64-bit register");
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ uint32_t s_red[THREADS / 32];
     __shared__ int64_t s_row;
-
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < COLS; i += THREADS) hist[i] = 0;
     uint64_t pres = 0;
-
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_row = (int64_t)atomicAdd(&scratch[0], 1);
@@ -150,64 +269,43 @@ k1_count(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets,
         if (row >= n) break;
         const int64_t beg = offsets[row];
         const int64_t L = offsets[row + 1] - beg;
-        uint4* out = reinterpret_cast<uint4*>(counts + row * ld);
+        uint32_t* out = counts + row * ld;
         if (L > KB_LONG_THRESHOLD) {
-            // queue for the split kernel; zero the row it will red.add into
             if (threadIdx.x == 0) {
                 const int slot = atomicAdd(&scratch[1], 1);
                 scratch[4 + slot] = (int32_t)row;
                 if (exotic_out) exotic_out[row] = 0;
             }
-            for (int i = threadIdx.x; i < VEC; i += THREADS) out[i] = make_uint4(0, 0, 0, 0);
+            for (int i = threadIdx.x; i < COLS / 4; i += THREADS) reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
             continue;
         }
-        const uint32_t ex = accumulate_range<KA, KB, PALB, THREADS>(bases, beg, L, 0, L, hist);
-        const uint32_t ex_total = block_sum(ex, s_red);        // contains the barrier after accumulation
+        const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB>(bases, beg, L, 0, L, hist, hist + COLS + threadIdx.x,
+                                                                  (beg & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
+        if (lane == 0) s_red[warp] = ex;
+        __syncthreads();                                         // all atomics done, s_red visible
         if (threadIdx.x == 0) {
+            uint32_t ex_total = 0;
+            for (int i = 0; i < THREADS / 32; ++i) ex_total += s_red[i];
             if (exotic_out) exotic_out[row] = ex_total;
-            if (ex_total) atomicAdd(reinterpret_cast<unsigned long long*>(scratch + 2), (unsigned long long)ex_total);
-        }
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int i = threadIdx.x + it * THREADS;
-            if (i < VEC) {
-                uint4 r;
-                if constexpr (PERMUTE) {
-                    const ushort4 p = *reinterpret_cast<const ushort4*>(perm + 4 * i);
-                    r = make_uint4(hist[p.x], hist[p.y], hist[p.z], hist[p.w]);
-                    hist[p.x] = 0; hist[p.y] = 0; hist[p.z] = 0; hist[p.w] = 0;
-                } else {
-                    r = *reinterpret_cast<uint4*>(hist + 4 * i);
-                    *reinterpret_cast<uint4*>(hist + 4 * i) = make_uint4(0, 0, 0, 0);
-                }
-                out[i] = r;
-                pres |= (uint64_t)((r.x != 0) | ((r.y != 0) << 1) | ((r.z != 0) << 2) | ((r.w != 0) << 3)) << (4 * it);
+            if (ex_total) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(scratch + 2), (unsigned long long)ex_total);
+                if (presence) presence[COLS] = 1u;
             }
         }
+        flush_row<COLS, PERMUTE, THREADS>(hist, out, perm, threadIdx.x, pres);
     }
-    if (presence) {
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int i = threadIdx.x + it * THREADS;
-            if (i < VEC) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((pres >> (4 * it + j)) & 1) presence[4 * i + j] = 1u;
-            }
-        }
-    }
+    publish_presence<COLS, THREADS>(presence, threadIdx.x, pres);
 }
 
-// Split path: every CTA walks the long-contig list and takes chunks blockIdx.x, +gridDim.x, ...
+// ---- split path: every CTA walks the long-contig list and takes chunks blockIdx.x, +gridDim.x, ...
 template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets,
               uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-              uint32_t* __restrict__ presence, const int32_t* __restrict__ scratch,
-              const uint16_t* __restrict__ perm) {
+              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     extern __shared__ __align__(16) uint32_t hist[];
-    __shared__ uint32_t s_red[THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_long = scratch[1];
     if (n_long == 0) return;
     for (int i = threadIdx.x; i < COLS; i += THREADS) hist[i] = 0;
@@ -220,12 +318,14 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
         for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
             const int64_t lo = c * KB_LONG_CHUNK;
             const int64_t hi = (lo + KB_LONG_CHUNK < L) ? lo + KB_LONG_CHUNK : L;
-            const uint32_t ex = accumulate_range<KA, KB, PALB, THREADS>(bases, beg, L, lo, hi, hist);
-            const uint32_t ex_total = block_sum(ex, s_red);
-            if (threadIdx.x == 0 && ex_total) {
-                if (exotic_out) atomicAdd(&exotic_out[row], ex_total);
-                atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<int32_t*>(scratch) + 2), (unsigned long long)ex_total);
+            const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB>(bases, beg, L, lo, hi, hist, hist + COLS + threadIdx.x,
+                                                                      ((beg + lo) & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
+            if (lane == 0 && ex) {
+                if (exotic_out) atomicAdd(&exotic_out[row], ex);
+                atomicAdd(reinterpret_cast<unsigned long long*>(scratch + 2), (unsigned long long)ex);
+                if (presence) presence[COLS] = 1u;
             }
+            __syncthreads();
             uint32_t* out = counts + row * ld;
             for (int i = threadIdx.x; i < COLS; i += THREADS) {
                 const int src = PERMUTE ? (int)perm[i] : i;
@@ -241,20 +341,15 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
     }
 }
 
-template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
+template <int KA, int KB, bool PALB, bool PERMUTE>
 int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_t n,
            uint32_t* d_counts, int64_t ld, uint32_t* d_exotic, uint32_t* d_presence,
            const uint16_t* d_perm) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
-    const size_t smem = (size_t)COLS * sizeof(uint32_t);
-    auto k1 = k1_count<KA, KB, PALB, PERMUTE, THREADS>;
-    auto k1l = k1_count_long<KA, KB, PALB, PERMUTE, THREADS>;
-    KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KB_CUDA(cudaFuncSetAttribute(k1l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, THREADS, smem));
-    if (per_sm < 1) { kb_set_error("k1_count does not fit on an SM"); return KB_ECUDA; }
-    // scratch: counter, n_long, up to n long rows
+    constexpr bool WARP_PER_CONTIG = COLS <= 2048;
+    constexpr int WARPS = 8;
+    constexpr int THREADS = (COLS > 8192) ? 256 : 128;            // CTA-per-contig / split kernels
+    // scratch: counter, n_long, exotic total, up to n long rows
     const int64_t need = n + 4;
     if (ctx->k1_scratch_cap < need) {
         if (ctx->d_k1_scratch) KB_CUDA(cudaFree(ctx->d_k1_scratch));
@@ -263,21 +358,44 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         ctx->k1_scratch_cap = need;
     }
     KB_CUDA(cudaMemsetAsync(ctx->d_k1_scratch, 0, 4 * sizeof(int32_t), ctx->stream));
-    int64_t grid = (int64_t)ctx->sm_count * per_sm;             // persistent: one resident wave
-    if (grid > n) grid = n;
-    if (grid < 1) grid = 1;
-    {
+    const size_t smem_one = (size_t)(COLS + THREADS) * sizeof(uint32_t);   // histogram + dummy words
+    if constexpr (WARP_PER_CONTIG) {
+        auto k1 = k1_count_warp<KA, KB, PALB, PERMUTE, WARPS>;
+        const size_t smem = (size_t)(COLS + 32) * sizeof(uint32_t) * WARPS;
+        KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, WARPS * 32, smem));
+        if (per_sm < 1) { kb_set_error("k1_count_warp does not fit on an SM"); return KB_ECUDA; }
+        int64_t grid = (int64_t)ctx->sm_count * per_sm;         // persistent: one resident wave
+        const int64_t want = (n + WARPS - 1) / WARPS;
+        if (grid > want) grid = want;
+        if (grid < 1) grid = 1;
         KbTimer t(ctx, 0);
-        k1<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                           d_presence, ctx->d_k1_scratch, d_perm);
+        k1<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
+                                                              d_presence, ctx->d_k1_scratch, d_perm);
+        ctx->launches++;
+    } else {
+        auto k1 = k1_count_cta<KA, KB, PALB, PERMUTE, THREADS>;
+        KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
+        int per_sm = 0;
+        KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, THREADS, smem_one));
+        if (per_sm < 1) { kb_set_error("k1_count_cta does not fit on an SM"); return KB_ECUDA; }
+        int64_t grid = (int64_t)ctx->sm_count * per_sm;
+        if (grid > n) grid = n;
+        if (grid < 1) grid = 1;
+        KbTimer t(ctx, 0);
+        k1<<<(unsigned)grid, THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
+                                                               d_presence, ctx->d_k1_scratch, d_perm);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());
     {
+        auto k1l = k1_count_long<KA, KB, PALB, PERMUTE, THREADS>;
+        KB_CUDA(cudaFuncSetAttribute(k1l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
         KbTimer t(ctx, 1);
-        k1l<<<(unsigned)(ctx->sm_count * 2), THREADS, smem, ctx->stream>>>(d_bases, d_offsets, d_counts, ld,
-                                                                          d_exotic, d_presence,
-                                                                          ctx->d_k1_scratch, d_perm);
+        k1l<<<(unsigned)(ctx->sm_count * 2), THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, d_counts, ld,
+                                                                              d_exotic, d_presence,
+                                                                              ctx->d_k1_scratch, d_perm);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());
@@ -318,19 +436,19 @@ int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases
         const uint16_t* perm = nullptr;
         int rc = build_perm_5p6(ctx->device, &perm);
         if (rc) return rc;
-        return launch<5, 6, true, true, 128>(KB_ARGS, perm);
+        return launch<5, 6, true, true>(KB_ARGS, perm);
     }
-    if (m.ka == 5 && m.kb == 6) return launch<5, 6, false, false, 128>(KB_ARGS, nullptr);
-    if (m.ka == 4 && m.kb == 5) return launch<4, 5, false, false, 128>(KB_ARGS, nullptr);
+    if (m.ka == 5 && m.kb == 6) return launch<5, 6, false, false>(KB_ARGS, nullptr);
+    if (m.ka == 4 && m.kb == 5) return launch<4, 5, false, false>(KB_ARGS, nullptr);
     if (m.kb == 0) {
         switch (m.ka) {
-            case 1: return launch<1, 0, false, false, 128>(KB_ARGS, nullptr);
-            case 2: return launch<2, 0, false, false, 128>(KB_ARGS, nullptr);
-            case 3: return launch<3, 0, false, false, 128>(KB_ARGS, nullptr);
-            case 4: return launch<4, 0, false, false, 128>(KB_ARGS, nullptr);
-            case 5: return launch<5, 0, false, false, 128>(KB_ARGS, nullptr);
-            case 6: return launch<6, 0, false, false, 128>(KB_ARGS, nullptr);
-            case 7: return launch<7, 0, false, false, 256>(KB_ARGS, nullptr);
+            case 1: return launch<1, 0, false, false>(KB_ARGS, nullptr);
+            case 2: return launch<2, 0, false, false>(KB_ARGS, nullptr);
+            case 3: return launch<3, 0, false, false>(KB_ARGS, nullptr);
+            case 4: return launch<4, 0, false, false>(KB_ARGS, nullptr);
+            case 5: return launch<5, 0, false, false>(KB_ARGS, nullptr);
+            case 6: return launch<6, 0, false, false>(KB_ARGS, nullptr);
+            case 7: return launch<7, 0, false, false>(KB_ARGS, nullptr);
         }
     }
 #undef KB_ARGS

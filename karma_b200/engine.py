@@ -207,7 +207,8 @@ class Engine:
 
     # ---- K1 ----------------------------------------------------------------------
     def count(self, d_bases, d_offsets, n, mode, counts=None, exotic=None, presence=None):
-        """u32 counts (n, D) [torch.int32 storage], exotic tallies (n,), presence (D,)."""
+        """u32 counts (n, D) [torch.int32 storage], exotic tallies (n,), presence (D+1,):
+        presence[c] != 0 iff column c occurs, presence[D] != 0 iff a window holds a non-ACGT byte."""
         self._bind_stream()
         cols = check(self.lib.kb_mode_columns(mode))
         if counts is None:
@@ -215,7 +216,7 @@ class Engine:
         if exotic is None:
             exotic = torch.empty(n, dtype=torch.int32, device=self.device)
         if presence is None:
-            presence = torch.empty(cols, dtype=torch.int32, device=self.device)
+            presence = torch.empty(cols + 1, dtype=torch.int32, device=self.device)
         presence.zero_()
         check(self.lib.kb_count(self.ctx, mode, ptr(d_bases), ptr(d_offsets), n, ptr(counts), counts.stride(0),
                                 ptr(exotic), ptr(presence)))
@@ -227,23 +228,19 @@ class Engine:
         return nl.value, ex.value
 
     # ---- K1x / K2: column dictionary ---------------------------------------------
-    def build_columns(self, mode, d_bases, d_offsets, n, counts, exotic, presence, exotic_total,
-                      group=None):
+    def build_columns(self, mode, d_bases, d_offsets, n, counts, exotic, presence, group=None):
         """kmer.py:146-179.  Returns (columns, counts') where columns is the sorted
-        list of observed k-mer strings and counts' the (n, D') matrix in that order."""
+        list of observed k-mer strings and counts' the (n, D') matrix in that order.
+        One collective (MAX over the presence vector, which also carries the
+        "non-ACGT window seen" flag) and one D2H copy."""
         self._bind_stream()
         names = mode_column_names(mode)
-        pres = presence
         if group is not None:
             import torch.distributed as dist
-            pres = presence.clone()
-            dist.all_reduce(pres, op=dist.ReduceOp.MAX, group=group)
-            t = torch.tensor([exotic_total], dtype=torch.int64, device=self.device)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            any_exotic = int(t.item()) > 0
-        else:
-            any_exotic = exotic_total > 0
-        present = pres.cpu().numpy() != 0
+            dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)
+        pres_h = presence.cpu().numpy()
+        present = pres_h[:len(names)] != 0
+        any_exotic = bool(pres_h[len(names)])
         keys = np.zeros(0, dtype=np.uint64)
         if any_exotic:
             nk, ne = c_int64(), c_int64()
@@ -279,20 +276,34 @@ class Engine:
         return columns, out[:, :d_out]
 
     # ---- K3 ------------------------------------------------------------------------
-    def normalise(self, counts, d_cols, d_key_len, want_profile=True, want_operand=True, profile=None):
+    def normalise(self, counts, d_cols, d_key_len, want_profile=True, want_operand=True, profile=None,
+                  rows_alloc=None):
+        """K3.  With ``rows_alloc`` > n the kNN inputs are allocated with that many rows
+        (the equal-size shard a rank contributes to the all-gather); the padding rows are
+        zero counts, key_len 1 and flagged so that they can never be neighbours."""
         self._bind_stream()
         n = counts.shape[0]
+        rows = n if rows_alloc is None else max(n, int(rows_alloc))
         ldp = d_cols
         if want_profile and profile is None:
             profile = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
         dp = (d_cols + 63) // 64 * 64
-        operand = torch.empty((n, dp), dtype=torch.float16, device=self.device) if want_operand else None
-        sqnorm = torch.empty(n, dtype=torch.float64, device=self.device)
-        rowflag = torch.empty(n, dtype=torch.uint8, device=self.device)
+        operand = torch.empty((rows, dp), dtype=torch.float16, device=self.device) if want_operand else None
+        sqnorm = torch.empty(rows, dtype=torch.float64, device=self.device)
+        rowflag = torch.empty(rows, dtype=torch.uint8, device=self.device)
+        key_len = d_key_len
+        if rows > n:
+            key_len = torch.empty(rows, dtype=torch.int32, device=self.device)
+            key_len[:n] = d_key_len[:n]
+            key_len[n:] = 1
+            if operand is not None:
+                operand[n:] = 0
+            sqnorm[n:] = 0
+            rowflag[n:] = 3
         check(self.lib.kb_normalise(self.ctx, ptr(counts), counts.stride(0), d_cols, ptr(d_key_len), n,
                                     ptr(profile) if want_profile else None, ldp,
                                     ptr(operand), dp, ptr(sqnorm), ptr(rowflag)))
-        return profile, operand, sqnorm, rowflag
+        return profile, operand, sqnorm, rowflag, key_len
 
     # ---- K4 + K5 ---------------------------------------------------------------------
     def knn(self, operand, key_len, sqnorm, rowflag, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False):
@@ -312,13 +323,81 @@ class Engine:
 
 
 # ---------------------------------------------------------------------------------------
-# whole path, host in -> host out  (what KmerClustering and bench.py's e2e leg call)
+# whole path
 # ---------------------------------------------------------------------------------------
+
+def all_gather_many(tensors, group):
+    """All-gather several equally-sharded tensors with one NCCL group launch where the
+    installed torch supports coalescing; plain back-to-back calls otherwise."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    outs = [torch.empty((t.shape[0] * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in tensors]
+    try:
+        with dist._coalescing_manager(group=group, device=tensors[0].device, async_ops=False):
+            for o, t in zip(outs, tensors):
+                dist.all_gather_into_tensor(o, t, group=group)
+    except Exception:
+        for o, t in zip(outs, tensors):
+            dist.all_gather_into_tensor(o, t, group=group)
+    return outs
+
+
+def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
+                want_profile=True, group=None, rank=0, world=1, n_total=None, gather_lists=False, bufs=None,
+                on_profile=None):
+    """The hot path on device-resident inputs: K1 -> column dictionary (-> K1x/K2) -> K3
+    [-> all-gather of the operand shards -> K4 -> K5].  Returns device tensors plus the
+    column list; nothing but the presence vector (and row flags) is copied to the host.
+    ``bufs``: optional dict of preallocated counts/exotic/presence tensors.
+    ``on_profile(profile)`` is called as soon as K3 has been enqueued (to start its D2H)."""
+    mode = mode_of(kmer_size)
+    b = bufs or {}
+    counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
+    faithful = mode == KB_MODE_5P6 or mode >= 16
+    if faithful:
+        columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence, group=group)
+    else:
+        if int(presence[-1].item()):
+            raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (some windows contain other bytes)")
+        columns = mode_column_names(mode)
+    d_cols = len(columns)
+    if d_cols == 0:
+        raise ZeroRowError(0)
+    if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
+        counts = counts.contiguous()
+    per = None
+    if group is not None and world > 1:
+        per = shard_bounds(n_total, world, rank)[2]
+    profile, operand, sqnorm, rowflag, key_len = engine.normalise(
+        counts, d_cols, d_key_len, want_profile=want_profile, want_operand=n_neighbors is not None, rows_alloc=per)
+    if on_profile is not None and profile is not None:
+        on_profile(profile)
+    out = {"columns": columns, "d_cols": d_cols, "counts": counts, "profile": profile, "operand": operand,
+           "sqnorm": sqnorm, "rowflag": rowflag, "idx": None, "dist": None}
+    if n_neighbors is None:
+        return out
+    if per is not None:
+        # the one exchange step: every rank needs all keys (operand + row metadata)
+        all_op, all_len, all_sq, all_fl = all_gather_many([operand, key_len, sqnorm, rowflag], group)
+        idx, dst, _ = engine.knn(all_op, all_len, all_sq, all_fl, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
+        if gather_lists:
+            pi = torch.full((per, n_neighbors), -1, dtype=torch.int32, device=engine.device)
+            pd = torch.zeros((per, n_neighbors), dtype=torch.float32, device=engine.device)
+            pi[:n] = idx
+            pd[:n] = dst
+            g_idx, g_dst = all_gather_many([pi, pd], group)
+            out.update(all_idx=g_idx, all_dist=g_dst)
+        out.update(all_rowflag=all_fl)
+    else:
+        idx, dst, _ = engine.knn(operand, key_len, sqnorm, rowflag, n_neighbors, impl=impl)
+    out.update(idx=idx, dist=dst)
+    return out
+
 
 def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbors=None,
                     impl=KB_KNN_AUTO, want_profile=True, group=None, rank=0, world=1, row0=0, n_total=None,
                     reuse_host=False):
-    """Run the hot path on host buffers.
+    """Run the hot path on host buffers (what KmerClustering and bench.py's e2e leg call).
 
     bases/offsets/key_len describe THIS rank's contigs (all of them when world==1).
     Returns dict(columns, profile (n,D') float64 ndarray or None, knn_idx, knn_dist)
@@ -330,68 +409,49 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
     ``reuse_host`` the pinned result buffers are owned by the engine and overwritten
     by the next call (a serving loop); otherwise every call returns fresh arrays.
     """
-    mode = mode_of(kmer_size)
     n = len(offsets) - 1
     d_bases, d_offsets, d_key_len = engine.upload(bases, offsets, key_len)
-    counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode)
-    faithful = mode == KB_MODE_5P6 or mode >= 16
-    _, ex_total = engine.count_stats()
-    if faithful:
-        columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence, ex_total,
-                                               group=group)
-    else:
-        if ex_total:
-            raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (%d windows contain other bytes)" % ex_total)
-        columns = mode_column_names(mode)
-    d_cols = len(columns)
-    if d_cols == 0:
-        raise ZeroRowError(0)
-    if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
-        counts = counts.contiguous()
-    profile, operand, sqnorm, rowflag = engine.normalise(counts, d_cols, d_key_len, want_profile=want_profile,
-                                                         want_operand=n_neighbors is not None)
     main = torch.cuda.current_stream(engine.device)
-    h_profile = None
-    if want_profile:
-        # D2H of the profile overlaps the kNN: side stream ordered after K3
-        h_profile = engine.host_buffer("profile", (n, d_cols), torch.float64, reuse_host)
-        side = engine.side_stream()
+    side = engine.side_stream()
+    hold = {}
+
+    def start_download(profile):
+        # D2H of the profile on the side stream, ordered after K3, overlapping the kNN
+        h = engine.host_buffer("profile", tuple(profile.shape), torch.float64, reuse_host)
         ready = torch.cuda.Event()
         ready.record(main)
         side.wait_event(ready)
         with torch.cuda.stream(side):
-            h_profile.copy_(profile, non_blocking=True)
+            h.copy_(profile, non_blocking=True)
         profile.record_stream(side)
-    flags = rowflag.cpu().numpy()
-    zero = np.flatnonzero(flags & 4)
+        hold["profile"] = h
+
+    r = device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors=n_neighbors, impl=impl,
+                    want_profile=want_profile, group=group, rank=rank, world=world, n_total=n_total,
+                    on_profile=start_download if want_profile else None)
+    flags_t = r.get("all_rowflag", r["rowflag"])
+    flags = flags_t.cpu().numpy()
+    own = r["rowflag"][:n].cpu().numpy() if "all_rowflag" in r else flags[:n]
+    zero = np.flatnonzero(own & 4)
     if len(zero):
         torch.cuda.synchronize(engine.device)
         raise ZeroRowError(int(zero[0]) + row0)
-    out = {"columns": columns, "profile": None, "knn_idx": None, "knn_dist": None,
-           "d_profile": profile, "d_operand": operand}
+    out = {"columns": r["columns"], "profile": None, "knn_idx": None, "knn_dist": None,
+           "d_profile": r["profile"], "d_operand": r["operand"]}
     if n_neighbors is not None:
-        if (flags & 3).any():
+        # padded index == global row, so the real rows of the gathered set are [0, n_total)
+        real = np.arange(len(flags)) < (n_total if "all_rowflag" in r else len(flags))
+        if ((flags & 3) != 0)[real].any():
             torch.cuda.synchronize(engine.device)
             raise _lib.KarmaB200Error(-6, "a k-mer count > 2048 or a squared norm >= 2^24 needs the exact side path (not built yet)")
-        if group is not None and world > 1:
-            # the one exchange step: every rank needs all keys (operand + row metadata);
-            # padding rows are flagged so they can never be candidates
-            _, _, per = shard_bounds(n_total, world, rank)
-            all_op = all_gather_padded(operand, n, per, group, 0)
-            all_len = all_gather_padded(d_key_len, n, per, group, 1)
-            all_sq = all_gather_padded(sqnorm, n, per, group, 0)
-            all_fl = all_gather_padded(rowflag, n, per, group, 3)
-            idx, dst, _ = engine.knn(all_op, all_len, all_sq, all_fl, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
-        else:
-            idx, dst, _ = engine.knn(operand, d_key_len, sqnorm, rowflag, n_neighbors, impl=impl)
-        h_idx = engine.host_buffer("knn_idx", tuple(idx.shape), torch.int32, reuse_host)
-        h_dst = engine.host_buffer("knn_dist", tuple(dst.shape), torch.float32, reuse_host)
-        h_idx.copy_(idx, non_blocking=True)
-        h_dst.copy_(dst, non_blocking=True)
+        h_idx = engine.host_buffer("knn_idx", tuple(r["idx"].shape), torch.int32, reuse_host)
+        h_dst = engine.host_buffer("knn_dist", tuple(r["dist"].shape), torch.float32, reuse_host)
+        h_idx.copy_(r["idx"], non_blocking=True)
+        h_dst.copy_(r["dist"], non_blocking=True)
         main.synchronize()
         out["knn_idx"] = h_idx.numpy()
         out["knn_dist"] = h_dst.numpy()
     if want_profile:
-        engine.side_stream().synchronize()
-        out["profile"] = h_profile.numpy()
+        side.synchronize()
+        out["profile"] = hold["profile"].numpy()
     return out

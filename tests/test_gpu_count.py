@@ -17,8 +17,10 @@ def _count(engine, bases, offsets, mode_name):
     d_bases, d_offsets, _ = engine.upload(bases, offsets, key_len)
     counts, exotic, presence = engine.count(d_bases, d_offsets, len(offsets) - 1, mode)
     torch.cuda.synchronize()
-    return (counts.cpu().numpy().view(np.uint32), exotic.cpu().numpy().view(np.uint32),
-            presence.cpu().numpy() != 0)
+    pres = presence.cpu().numpy() != 0
+    ex = exotic.cpu().numpy().view(np.uint32)
+    assert pres[-1] == (ex.sum() > 0), "presence[D] must flag non-ACGT windows"
+    return counts.cpu().numpy().view(np.uint32), ex, pres[:-1]
 
 
 @pytest.mark.parametrize("mode", ["5p6", "5+6", "4+5", 1, 2, 3, 4, 5, 6, 7])

@@ -73,7 +73,7 @@ def test_tensor_core_gram_is_exact(engine):
     mode = mode_of("5p6")
     d_bases, d_offsets, d_len = engine.upload(asm.bases, asm.offsets, asm.key_len)
     counts, _, _ = engine.count(d_bases, d_offsets, asm.n, mode)
-    _, operand, sqnorm, rowflag = engine.normalise(counts, 1088, d_len, want_profile=False)
+    _, operand, sqnorm, rowflag, _ = engine.normalise(counts, 1088, d_len, want_profile=False)
     k = 24
     idx, dist, d2 = engine.knn(operand, d_len, sqnorm, rowflag, k, impl=_lib.KB_KNN_TC, want_d2=True)
     torch.cuda.synchronize()
@@ -94,7 +94,7 @@ def test_query_shard_equals_full(engine):
     mode = mode_of("5p6")
     d_bases, d_offsets, d_len = engine.upload(asm.bases, asm.offsets, asm.key_len)
     counts, _, _ = engine.count(d_bases, d_offsets, asm.n, mode)
-    _, operand, sqnorm, rowflag = engine.normalise(counts, 1088, d_len, want_profile=False)
+    _, operand, sqnorm, rowflag, _ = engine.normalise(counts, 1088, d_len, want_profile=False)
     full_i, full_d, _ = engine.knn(operand, d_len, sqnorm, rowflag, 5, impl=_lib.KB_KNN_TC)
     part_i, part_d, _ = engine.knn(operand, d_len, sqnorm, rowflag, 5, q_row0=250, nq=333, impl=_lib.KB_KNN_TC)
     assert torch.equal(full_i[250:583], part_i) and torch.equal(full_d[250:583], part_d)
