@@ -34,6 +34,16 @@ extern "C" {
 
 typedef struct kb_ctx kb_ctx;
 
+/* Per-contig metadata of the kNN stage, produced by kb_normalise, consumed by kb_knn.
+ * One 16-byte record per row, so that a row shard travels in ONE all-gather. */
+typedef struct kb_rowmeta {
+    double  sqnorm;   /* sum_c count^2 (exact integer)                                   */
+    int32_t key_len;  /* len(header key incl. '>'), what kmer.py:213 divides by          */
+    int32_t flags;    /* bit0: some count > 2048 (fp16 operand saturated)
+                         bit1: sqnorm >= 2^24 (fp32 Gram not exact)
+                         bit2: all-zero row (kmer.py:250-258 exits)                      */
+} kb_rowmeta;
+
 /* error codes */
 #define KB_OK            0
 #define KB_EINVAL       -1   /* bad argument                                  */
@@ -146,15 +156,12 @@ KB_API int kb_compact(kb_ctx* ctx, const uint32_t* d_in, int64_t ld_in, int32_t 
  *  d_operand  fp16 [n*ld_operand]   raw counts as fp16 (exact <= 2048), columns
  *                                   [d_cols, ld_operand) zero-filled;
  *                                   ld_operand % 64 == 0
- *  d_sqnorm   double[n]             sum_c count^2 (exact integer)
- *  d_rowflag  uint8[n]              bit0: some count > 2048 (operand saturated),
- *                                   bit1: sqnorm >= 2^24 (fp32 Gram not exact),
- *                                   bit2: all-zero row (kmer.py:250-258 exits) */
+ *  d_rowmeta  kb_rowmeta[n]         squared norm, key length and flags per row */
 KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32_t d_cols,
                  const int32_t* d_key_len, int64_t n,
                  double* d_profile, int64_t ld_profile,
                  void* d_operand, int64_t ld_operand,
-                 double* d_sqnorm, uint8_t* d_rowflag);
+                 kb_rowmeta* d_rowmeta);
 
 /* ---- K4 + K5: exact kNN ----------------------------------------------------
  * Replaces the neighbour search inside umap.UMAP(...).fit_transform at
@@ -169,12 +176,12 @@ KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32
  *   d2 = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2     (fp64)
  * and orders by (self first, d2, index).  d_dist receives sqrt(d2) as float
  * (UMAP's knn_dists), d_d2 (nullable) the fp64 squared distances.
- * Rows whose KB rowflag bits 0/1 are set are rejected with KB_EOVERFLOW unless
- * the exact side path is enabled (see kb_knn_flags).                          */
+ * Rows whose flags bit0/bit1 are set (and padding rows of a multi-rank gather, which
+ * carry both) are never candidates; the caller must route them elsewhere.      */
 KB_API int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl);
 KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
            const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
-           const int32_t* d_key_len, const double* d_sqnorm, const uint8_t* d_rowflag,
+           const kb_rowmeta* d_rowmeta,
            int64_t nk, int64_t q_row0, int64_t nq,
            int32_t* d_idx, float* d_dist, double* d_d2,
            void* d_workspace, int64_t workspace_bytes);

@@ -45,9 +45,9 @@ SIGNATURES = {
     "kb_exotic_fetch": (c_int, [_P, _P, _P, _P, _P]),
     "kb_exotic_scatter": (c_int, [_P, _P, _P, c_int64]),
     "kb_compact": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32]),
-    "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P]),
+    "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
     "kb_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32, c_int]),
-    "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, _P, _P, c_int64, c_int64, c_int64,
+    "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int64,
                        _P, _P, _P, _P, c_int64]),
     "kb_enable_timing": (c_int, [_P, c_int]),
     "kb_stage_ms": (c_int, [_P, c_int, POINTER(c_float), POINTER(c_int)]),

@@ -40,17 +40,19 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, KbKnn
 namespace {
 
 __global__ void __launch_bounds__(256)
-k4_prep_colmeta(const int32_t* __restrict__ key_len, const double* __restrict__ sqnorm,
-                const uint8_t* __restrict__ rowflag, int64_t nk, int64_t nk_pad, float2* __restrict__ colmeta,
+k4_prep_colmeta(const kb_rowmeta* __restrict__ rowmeta, int64_t nk, int64_t nk_pad, float2* __restrict__ colmeta,
                 int32_t* __restrict__ row_thr, int64_t nq) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nq) row_thr[j] = 0x7f800000;                      // +inf as an ordered-int key
     if (j >= nk_pad) return;
     float2 cm;
-    if (j < nk && !(rowflag && (rowflag[j] & 3))) {
-        const double l = (double)key_len[j];
+    kb_rowmeta m;
+    m.flags = 3;
+    if (j < nk) m = rowmeta[j];
+    if (!(m.flags & 3)) {
+        const double l = (double)m.key_len;
         cm.x = (float)(-2.0 / l);
-        cm.y = (float)(sqnorm[j] / (l * l));
+        cm.y = (float)(m.sqnorm / (l * l));
     } else {
         cm.x = 0.f;
         cm.y = __int_as_float(0x7f800000);                    // +inf: never a candidate
@@ -64,7 +66,7 @@ k4_prep_colmeta(const int32_t* __restrict__ key_len, const double* __restrict__ 
 template <int KP>
 __global__ void __launch_bounds__(256)
 k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
-        const float2* __restrict__ colmeta, const int32_t* __restrict__ key_len,
+        const float2* __restrict__ colmeta, const kb_rowmeta* __restrict__ rowmeta,
         int64_t nk, int64_t q_row0, int64_t nq, int splits, int64_t n_tiles,
         float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
     constexpr int BM = 64, BN = 64, BK = 32;
@@ -88,7 +90,7 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
     if (tid < BM) {
         list.init(tid);
         const int64_t q = m0 + tid;
-        if (q < nq) my_len = (float)key_len[q_row0 + q];
+        if (q < nq) my_len = (float)rowmeta[q_row0 + q].key_len;
     }
     const int lrow = tid >> 2, lseg = (tid & 3) * 8;
     for (int64_t t = t_lo; t < t_hi; ++t) {
@@ -150,7 +152,7 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
 template <int KP>
 __global__ void __launch_bounds__(256)
 k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
-                const int32_t* __restrict__ key_len, int64_t q_row0, int64_t nq, int splits, int32_t k,
+                const kb_rowmeta* __restrict__ rowmeta, int64_t q_row0, int64_t nq, int splits, int32_t k,
                 const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist, double* __restrict__ out_d2) {
     constexpr int MAXC = 16;                                  // splits*KP <= 32*MAXC
@@ -195,13 +197,13 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
     if (!has_self && lane == KP - 1) my_idx = self;
     // ---- 3. exact distances: all lanes cooperate on one candidate at a time
     const __half* qrow = op + (int64_t)self * ld;
-    const double lq = (double)key_len[self];
+    const double lq = (double)rowmeta[self].key_len;
     double my_d2 = 0.0;
     for (int e = 0; e < KP; ++e) {
         const int32_t j = __shfl_sync(0xffffffffu, my_idx, e);
         if (j < 0) continue;
         const __half* krow = op + (int64_t)j * ld;
-        const double lj = (double)key_len[j];
+        const double lj = (double)rowmeta[j].key_len;
         double acc = 0.0;
         for (int c = 8 * lane; c < dp; c += 256) {
             const uint4 a = *reinterpret_cast<const uint4*>(qrow + c);
@@ -246,10 +248,10 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 
 template <int KP>
 int run_simt(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp,
-             const int32_t* key_len, int64_t nk, int64_t q_row0, int64_t nq, uint8_t* ws) {
+             const kb_rowmeta* rowmeta, int64_t nk, int64_t q_row0, int64_t nq, uint8_t* ws) {
     dim3 grid((unsigned)p.m_blocks, (unsigned)p.splits);
     k4_simt<KP><<<grid, 256, 0, ctx->stream>>>(op, ld, dp, reinterpret_cast<const float2*>(ws + p.off_colmeta),
-                                              key_len, nk, q_row0, nq, p.splits, p.n_tiles,
+                                              rowmeta, nk, q_row0, nq, p.splits, p.n_tiles,
                                               reinterpret_cast<float*>(ws + p.off_score),
                                               reinterpret_cast<int32_t*>(ws + p.off_idx));
     ctx->launches++;
@@ -259,11 +261,11 @@ int run_simt(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int3
 
 template <int KP>
 int run_rerank(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp,
-               const int32_t* key_len, int64_t q_row0, int64_t nq, int32_t k, uint8_t* ws,
+               const kb_rowmeta* rowmeta, int64_t q_row0, int64_t nq, int32_t k, uint8_t* ws,
                int32_t* d_idx, float* d_dist, double* d_d2) {
     const int64_t grid = (nq + 7) / 8;
     k5_merge_rerank<KP><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-        op, ld, dp, key_len, q_row0, nq, p.splits, k, reinterpret_cast<const float*>(ws + p.off_score),
+        op, ld, dp, rowmeta, q_row0, nq, p.splits, k, reinterpret_cast<const float*>(ws + p.off_score),
         reinterpret_cast<const int32_t*>(ws + p.off_idx), d_idx, d_dist, d_d2);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
@@ -286,11 +288,11 @@ extern "C" int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int
 
 extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
                       const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
-                      const int32_t* d_key_len, const double* d_sqnorm, const uint8_t* d_rowflag,
+                      const kb_rowmeta* d_rowmeta,
                       int64_t nk, int64_t q_row0, int64_t nq,
                       int32_t* d_idx, float* d_dist, double* d_d2,
                       void* d_workspace, int64_t workspace_bytes) {
-    KB_CHECK_ARG(ctx && d_operand && d_key_len && d_sqnorm && d_idx && d_dist && d_workspace, "null pointer");
+    KB_CHECK_ARG(ctx && d_operand && d_rowmeta && d_idx && d_dist && d_workspace, "null pointer");
     KB_CHECK_ARG(d_cols_padded > 0 && (d_cols_padded % 64) == 0 && ld_operand >= d_cols_padded && (ld_operand % 8) == 0,
                  "operand columns must be padded to a multiple of 64");
     KB_CHECK_ARG(((uintptr_t)d_operand % 16) == 0, "operand must be 16-byte aligned");
@@ -308,19 +310,19 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
     const __half* op = reinterpret_cast<const __half*>(d_operand);
 
     k4_prep_colmeta<<<(unsigned)((p.nk_pad + 255) / 256), 256, 0, ctx->stream>>>(
-        d_key_len, d_sqnorm, d_rowflag, nk, p.nk_pad, reinterpret_cast<float2*>(ws + p.off_colmeta),
+        d_rowmeta, nk, p.nk_pad, reinterpret_cast<float2*>(ws + p.off_colmeta),
         reinterpret_cast<int32_t*>(ws + p.off_rowthr), nq);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     {
         KbTimer t(ctx, 4);
         if (impl == KB_KNN_TC) {
-            rc = kb_knn_tc_launch(ctx, p, d_operand, ld_operand, d_cols_padded, d_key_len, nk, q_row0, nq, ws);
+            rc = kb_knn_tc_launch(ctx, p, d_operand, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws);
         } else {
             switch (p.kp) {
-                case 8: rc = run_simt<8>(ctx, p, op, ld_operand, d_cols_padded, d_key_len, nk, q_row0, nq, ws); break;
-                case 16: rc = run_simt<16>(ctx, p, op, ld_operand, d_cols_padded, d_key_len, nk, q_row0, nq, ws); break;
-                default: rc = run_simt<32>(ctx, p, op, ld_operand, d_cols_padded, d_key_len, nk, q_row0, nq, ws); break;
+                case 8: rc = run_simt<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
+                case 16: rc = run_simt<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
+                default: rc = run_simt<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
             }
         }
         if (rc) return rc;
@@ -328,9 +330,9 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
     {
         KbTimer t(ctx, 5);
         switch (p.kp) {
-            case 8: rc = run_rerank<8>(ctx, p, op, ld_operand, d_cols_padded, d_key_len, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
-            case 16: rc = run_rerank<16>(ctx, p, op, ld_operand, d_cols_padded, d_key_len, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
-            default: rc = run_rerank<32>(ctx, p, op, ld_operand, d_cols_padded, d_key_len, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
+            case 8: rc = run_rerank<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
+            case 16: rc = run_rerank<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
+            default: rc = run_rerank<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
         }
     }
     return rc;

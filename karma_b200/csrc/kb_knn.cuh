@@ -50,5 +50,5 @@ struct KbRowList {
 };
 
 int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int64_t ld_operand,
-                     int32_t d_cols_padded, const int32_t* d_key_len, int64_t nk, int64_t q_row0,
+                     int32_t d_cols_padded, const kb_rowmeta* d_rowmeta, int64_t nk, int64_t q_row0,
                      int64_t nq, uint8_t* ws);

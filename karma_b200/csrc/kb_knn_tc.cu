@@ -119,7 +119,7 @@ struct TcParams {
     int splits;
     int k_blocks;                     // Dp / 64
     const float2* colmeta;
-    const int32_t* key_len;
+    const kb_rowmeta* rowmeta;
     float* cand_score;
     int32_t* cand_idx;
     int32_t* row_thr;                 // per query row: best known KP-th score (ordered-int key), shared by all units
@@ -270,7 +270,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             const Unit un(p, u);
             const int64_t q = un.mb * BM + r;
             const bool live = q < p.nq;
-            const float li = live ? (float)p.key_len[p.q_row0 + q] : 1.f;
+            const float li = live ? (float)p.rowmeta[p.q_row0 + q].key_len : 1.f;
             list.init(r);
             float thr = __int_as_float(0x7f800000);          // min(own KP-th best, row_thr): the prune bound
             float own = thr; int pos = 0;                    // own list's worst entry and its slot
@@ -359,7 +359,7 @@ int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int64_t
 }  // namespace
 
 int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int64_t ld_operand,
-                     int32_t d_cols_padded, const int32_t* d_key_len, int64_t nk, int64_t q_row0,
+                     int32_t d_cols_padded, const kb_rowmeta* d_rowmeta, int64_t nk, int64_t q_row0,
                      int64_t nq, uint8_t* ws) {
     if (!ctx->encode_tiled) {
         void* fn = nullptr;
@@ -383,7 +383,7 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
     prm.m_blocks = p.m_blocks; prm.n_tiles = p.n_tiles; prm.splits = p.splits;
     prm.k_blocks = d_cols_padded / BK;
     prm.colmeta = reinterpret_cast<const float2*>(ws + p.off_colmeta);
-    prm.key_len = d_key_len;
+    prm.rowmeta = d_rowmeta;
     prm.cand_score = reinterpret_cast<float*>(ws + p.off_score);
     prm.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
     prm.row_thr = reinterpret_cast<int32_t*>(ws + p.off_rowthr);

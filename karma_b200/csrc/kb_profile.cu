@@ -35,7 +35,7 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
              const int32_t* __restrict__ key_len, int64_t n,
              double* __restrict__ profile, int64_t ld_profile,
              __half* __restrict__ operand, int64_t ld_operand,
-             double* __restrict__ sqnorm, uint8_t* __restrict__ rowflag) {
+             kb_rowmeta* __restrict__ rowmeta) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -87,8 +87,13 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
         if (lane == 0) {
-            if (sqnorm) sqnorm[row] = (double)sq;
-            if (rowflag) rowflag[row] = (uint8_t)((mx > 2048u ? 1 : 0) | (sq >= (1ull << 24) ? 2 : 0) | (mx == 0 ? 4 : 0));
+            if (rowmeta) {
+                kb_rowmeta m;
+                m.sqnorm = (double)sq;
+                m.key_len = key_len[row];
+                m.flags = (mx > 2048u ? 1 : 0) | (sq >= (1ull << 24) ? 2 : 0) | (mx == 0 ? 4 : 0);
+                rowmeta[row] = m;
+            }
         }
     }
 }
@@ -114,7 +119,7 @@ extern "C" int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, i
                             const int32_t* d_key_len, int64_t n,
                             double* d_profile, int64_t ld_profile,
                             void* d_operand, int64_t ld_operand,
-                            double* d_sqnorm, uint8_t* d_rowflag) {
+                            kb_rowmeta* d_rowmeta) {
     KB_CHECK_ARG(ctx && d_counts && d_key_len, "null pointer");
     KB_CHECK_ARG(n >= 0 && d_cols > 0 && ld >= d_cols, "shape");
     KB_CHECK_ARG((ld % 4) == 0 && ((uintptr_t)d_counts % 16) == 0, "counts must be 16-byte aligned with ld % 4 == 0");
@@ -127,7 +132,7 @@ extern "C" int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, i
     const int64_t grid = blocks_needed < (int64_t)ctx->sm_count * 8 ? blocks_needed : (int64_t)ctx->sm_count * 8;
     k3_normalise<<<(unsigned)grid, 256, 0, ctx->stream>>>(d_counts, ld, d_cols, d_key_len, n, d_profile, ld_profile,
                                                           reinterpret_cast<__half*>(d_operand), ld_operand,
-                                                          d_sqnorm, d_rowflag);
+                                                          d_rowmeta);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;

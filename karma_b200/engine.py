@@ -289,24 +289,19 @@ class Engine:
             profile = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
         dp = (d_cols + 63) // 64 * 64
         operand = torch.empty((rows, dp), dtype=torch.float16, device=self.device) if want_operand else None
-        sqnorm = torch.empty(rows, dtype=torch.float64, device=self.device)
-        rowflag = torch.empty(rows, dtype=torch.uint8, device=self.device)
-        key_len = d_key_len
+        # kb_rowmeta records (16 B): [sqnorm f64 | key_len i32 | flags i32] viewed as int32 x 4
+        rowmeta = torch.empty((rows, 4), dtype=torch.int32, device=self.device)
         if rows > n:
-            key_len = torch.empty(rows, dtype=torch.int32, device=self.device)
-            key_len[:n] = d_key_len[:n]
-            key_len[n:] = 1
             if operand is not None:
                 operand[n:] = 0
-            sqnorm[n:] = 0
-            rowflag[n:] = 3
+            rowmeta[n:] = torch.tensor([0, 0, 1, 3], dtype=torch.int32, device=self.device)
         check(self.lib.kb_normalise(self.ctx, ptr(counts), counts.stride(0), d_cols, ptr(d_key_len), n,
                                     ptr(profile) if want_profile else None, ldp,
-                                    ptr(operand), dp, ptr(sqnorm), ptr(rowflag)))
-        return profile, operand, sqnorm, rowflag, key_len
+                                    ptr(operand), dp, ptr(rowmeta)))
+        return profile, operand, rowmeta
 
     # ---- K4 + K5 ---------------------------------------------------------------------
-    def knn(self, operand, key_len, sqnorm, rowflag, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False):
+    def knn(self, operand, rowmeta, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False):
         self._bind_stream()
         nk, dp = operand.shape
         nq = nk - q_row0 if nq is None else nq
@@ -316,8 +311,8 @@ class Engine:
         idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
         dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         d2 = torch.empty((nq, k), dtype=torch.float64, device=self.device) if want_d2 else None
-        check(self.lib.kb_knn(self.ctx, impl, k, ptr(operand), operand.stride(0), dp, ptr(key_len), ptr(sqnorm),
-                              ptr(rowflag), nk, q_row0, nq, ptr(idx), ptr(dist), ptr(d2),
+        check(self.lib.kb_knn(self.ctx, impl, k, ptr(operand), operand.stride(0), dp, ptr(rowmeta),
+                              nk, q_row0, nq, ptr(idx), ptr(dist), ptr(d2),
                               ptr(self._ws), self._ws.numel()))
         return idx, dist, d2
 
@@ -326,20 +321,13 @@ class Engine:
 # whole path
 # ---------------------------------------------------------------------------------------
 
-def all_gather_many(tensors, group):
-    """All-gather several equally-sharded tensors with one NCCL group launch where the
-    installed torch supports coalescing; plain back-to-back calls otherwise."""
+def all_gather_rows(t, group):
+    """All-gather equal row shards into one (rows*world, ...) tensor."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    outs = [torch.empty((t.shape[0] * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in tensors]
-    try:
-        with dist._coalescing_manager(group=group, device=tensors[0].device, async_ops=False):
-            for o, t in zip(outs, tensors):
-                dist.all_gather_into_tensor(o, t, group=group)
-    except Exception:
-        for o, t in zip(outs, tensors):
-            dist.all_gather_into_tensor(o, t, group=group)
-    return outs
+    out = torch.empty((t.shape[0] * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out
 
 
 def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
@@ -368,28 +356,32 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
     per = None
     if group is not None and world > 1:
         per = shard_bounds(n_total, world, rank)[2]
-    profile, operand, sqnorm, rowflag, key_len = engine.normalise(
+    profile, operand, rowmeta = engine.normalise(
         counts, d_cols, d_key_len, want_profile=want_profile, want_operand=n_neighbors is not None, rows_alloc=per)
     if on_profile is not None and profile is not None:
         on_profile(profile)
     out = {"columns": columns, "d_cols": d_cols, "counts": counts, "profile": profile, "operand": operand,
-           "sqnorm": sqnorm, "rowflag": rowflag, "idx": None, "dist": None}
+           "rowmeta": rowmeta, "idx": None, "dist": None}
     if n_neighbors is None:
         return out
     if per is not None:
-        # the one exchange step: every rank needs all keys (operand + row metadata)
-        all_op, all_len, all_sq, all_fl = all_gather_many([operand, key_len, sqnorm, rowflag], group)
-        idx, dst, _ = engine.knn(all_op, all_len, all_sq, all_fl, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
+        # the one exchange step: every rank needs all keys -- two collectives, the fp16
+        # operand shards and the 16-byte row records
+        all_op = all_gather_rows(operand, group)
+        all_meta = all_gather_rows(rowmeta, group)
+        idx, dst, _ = engine.knn(all_op, all_meta, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
         if gather_lists:
-            pi = torch.full((per, n_neighbors), -1, dtype=torch.int32, device=engine.device)
-            pd = torch.zeros((per, n_neighbors), dtype=torch.float32, device=engine.device)
-            pi[:n] = idx
-            pd[:n] = dst
-            g_idx, g_dst = all_gather_many([pi, pd], group)
-            out.update(all_idx=g_idx, all_dist=g_dst)
-        out.update(all_rowflag=all_fl)
+            # k-lists back to every rank: [idx | dist bits] packed per row, one collective
+            packed = torch.empty((per, 2 * n_neighbors), dtype=torch.int32, device=engine.device)
+            if per > n:
+                packed[n:] = -1
+            packed[:n, :n_neighbors] = idx
+            packed[:n, n_neighbors:] = dst.view(torch.int32)
+            g = all_gather_rows(packed, group)
+            out.update(all_idx=g[:, :n_neighbors], all_dist=g[:, n_neighbors:].view(torch.float32))
+        out.update(all_rowmeta=all_meta)
     else:
-        idx, dst, _ = engine.knn(operand, key_len, sqnorm, rowflag, n_neighbors, impl=impl)
+        idx, dst, _ = engine.knn(operand, rowmeta, n_neighbors, impl=impl)
     out.update(idx=idx, dist=dst)
     return out
 
@@ -429,9 +421,9 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
     r = device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors=n_neighbors, impl=impl,
                     want_profile=want_profile, group=group, rank=rank, world=world, n_total=n_total,
                     on_profile=start_download if want_profile else None)
-    flags_t = r.get("all_rowflag", r["rowflag"])
-    flags = flags_t.cpu().numpy()
-    own = r["rowflag"][:n].cpu().numpy() if "all_rowflag" in r else flags[:n]
+    gathered = "all_rowmeta" in r
+    flags = r["all_rowmeta" if gathered else "rowmeta"][:, 3].cpu().numpy()
+    own = r["rowmeta"][:n, 3].cpu().numpy() if gathered else flags[:n]
     zero = np.flatnonzero(own & 4)
     if len(zero):
         torch.cuda.synchronize(engine.device)
@@ -440,7 +432,7 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
            "d_profile": r["profile"], "d_operand": r["operand"]}
     if n_neighbors is not None:
         # padded index == global row, so the real rows of the gathered set are [0, n_total)
-        real = np.arange(len(flags)) < (n_total if "all_rowflag" in r else len(flags))
+        real = np.arange(len(flags)) < (n_total if gathered else len(flags))
         if ((flags & 3) != 0)[real].any():
             torch.cuda.synchronize(engine.device)
             raise _lib.KarmaB200Error(-6, "a k-mer count > 2048 or a squared norm >= 2^24 needs the exact side path (not built yet)")

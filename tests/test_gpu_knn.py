@@ -73,9 +73,9 @@ def test_tensor_core_gram_is_exact(engine):
     mode = mode_of("5p6")
     d_bases, d_offsets, d_len = engine.upload(asm.bases, asm.offsets, asm.key_len)
     counts, _, _ = engine.count(d_bases, d_offsets, asm.n, mode)
-    _, operand, sqnorm, rowflag, _ = engine.normalise(counts, 1088, d_len, want_profile=False)
+    _, operand, rowmeta = engine.normalise(counts, 1088, d_len, want_profile=False)
     k = 24
-    idx, dist, d2 = engine.knn(operand, d_len, sqnorm, rowflag, k, impl=_lib.KB_KNN_TC, want_d2=True)
+    idx, dist, d2 = engine.knn(operand, rowmeta, k, impl=_lib.KB_KNN_TC, want_d2=True)
     torch.cuda.synchronize()
     c = counts.cpu().numpy().view(np.uint32).astype(np.int64)
     gram = c @ c.T
@@ -94,9 +94,9 @@ def test_query_shard_equals_full(engine):
     mode = mode_of("5p6")
     d_bases, d_offsets, d_len = engine.upload(asm.bases, asm.offsets, asm.key_len)
     counts, _, _ = engine.count(d_bases, d_offsets, asm.n, mode)
-    _, operand, sqnorm, rowflag, _ = engine.normalise(counts, 1088, d_len, want_profile=False)
-    full_i, full_d, _ = engine.knn(operand, d_len, sqnorm, rowflag, 5, impl=_lib.KB_KNN_TC)
-    part_i, part_d, _ = engine.knn(operand, d_len, sqnorm, rowflag, 5, q_row0=250, nq=333, impl=_lib.KB_KNN_TC)
+    _, operand, rowmeta = engine.normalise(counts, 1088, d_len, want_profile=False)
+    full_i, full_d, _ = engine.knn(operand, rowmeta, 5, impl=_lib.KB_KNN_TC)
+    part_i, part_d, _ = engine.knn(operand, rowmeta, 5, q_row0=250, nq=333, impl=_lib.KB_KNN_TC)
     assert torch.equal(full_i[250:583], part_i) and torch.equal(full_d[250:583], part_d)
 
 
