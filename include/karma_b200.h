@@ -163,6 +163,10 @@ KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32
                  void* d_operand, int64_t ld_operand,
                  kb_rowmeta* d_rowmeta);
 
+/* OR of kb_rowmeta.flags over rows [0,n) (padding rows, bit3, excluded) into *d_out:
+ * lets the host validate a whole pass by reading one word. */
+KB_API int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t n, uint32_t* d_out);
+
 /* ---- K4 + K5: exact kNN ----------------------------------------------------
  * Replaces the neighbour search inside umap.UMAP(...).fit_transform at
  * kmer.py:285-290 (euclidean metric over the profile rows, the point itself
@@ -176,13 +180,19 @@ KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32
  *   d2 = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2     (fp64)
  * and orders by (self first, d2, index).  d_dist receives sqrt(d2) as float
  * (UMAP's knn_dists), d_d2 (nullable) the fp64 squared distances.
- * Rows whose flags bit0/bit1 are set (and padding rows of a multi-rank gather, which
- * carry both) are never candidates; the caller must route them elsewhere.      */
-KB_API int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl);
+ * Exact side path (K4x): rows whose flags bit0/bit1 are set cannot be scored exactly by
+ * the tensor path; they are masked there and handled in fp64 from their true counts:
+ *  d_flag_rows   int32[n_flag]  ascending key-row indices of ALL flagged rows
+ *  d_flag_counts uint32[n_flag*ld_flag_counts]  their count rows (flag_cols columns)
+ * (both NULL / 0 when no row is flagged).  Padding rows of a multi-rank gather carry
+ * flags = 3|8 and are never candidates.                                         */
+KB_API int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl, int64_t n_flag);
 KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
            const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
            const kb_rowmeta* d_rowmeta,
            int64_t nk, int64_t q_row0, int64_t nq,
+           const int32_t* d_flag_rows, const uint32_t* d_flag_counts, int64_t ld_flag_counts,
+           int32_t flag_cols, int64_t n_flag,
            int32_t* d_idx, float* d_dist, double* d_d2,
            void* d_workspace, int64_t workspace_bytes);
 
@@ -190,7 +200,7 @@ KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
  * by a CUDA-event pair on the context stream (a ring of 128 pairs per stage).
  * kb_stage_ms synchronises, returns the mean duration (ms) and the number of launches
  * recorded since the last read, and resets the stage.
- *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank */
+ *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank, 6 exact side path */
 KB_API int kb_enable_timing(kb_ctx* ctx, int on);
 KB_API int kb_stage_ms(kb_ctx* ctx, int which, float* mean_ms, int* n_launches);
 /* Number of kernels this library launched since the context was created. */

@@ -17,7 +17,7 @@ KB_MODE_DENSE_4_5 = 2
 KB_KNN_AUTO, KB_KNN_SIMT, KB_KNN_TC = 0, 1, 2
 KB_ENOGPU = -3
 
-STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5}
+STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5, "knn_exact": 6}
 
 
 def KB_MODE_K(k):
@@ -46,9 +46,10 @@ SIGNATURES = {
     "kb_exotic_scatter": (c_int, [_P, _P, _P, c_int64]),
     "kb_compact": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32]),
     "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
-    "kb_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32, c_int]),
+    "kb_rowmeta_flags_or": (c_int, [_P, _P, c_int64, _P]),
+    "kb_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32, c_int, c_int64]),
     "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int64,
-                       _P, _P, _P, _P, c_int64]),
+                       _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64]),
     "kb_enable_timing": (c_int, [_P, c_int]),
     "kb_stage_ms": (c_int, [_P, c_int, POINTER(c_float), POINTER(c_int)]),
     "kb_launch_count": (c_int64, [_P]),

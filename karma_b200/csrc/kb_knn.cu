@@ -13,7 +13,7 @@
 #include "kb_knn.cuh"
 #include <math.h>
 
-int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, KbKnnPlan* p) {
+int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64_t n_flag, KbKnnPlan* p) {
     if (k < 1 || nq < 1 || nk < 1 || k > nk) { kb_set_error("kNN: need 1 <= k <= nk and nq >= 1"); return KB_EINVAL; }
     if (k > 24) { kb_set_error("kNN: n_neighbors > 24 not built (candidate lists are <= 32 wide)"); return KB_EUNSUPPORTED; }
     p->impl = impl;
@@ -33,6 +33,8 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, KbKnn
     p->off_score = off;   off += kb_round_up(nq * p->splits * p->kp * (int64_t)sizeof(float), 256);
     p->off_idx = off;     off += kb_round_up(nq * p->splits * p->kp * (int64_t)sizeof(int32_t), 256);
     p->off_rowthr = off;  off += kb_round_up(nq * (int64_t)sizeof(int32_t), 256);
+    p->off_xidx = off;    off += n_flag > 0 ? kb_round_up(nq * p->kp * (int64_t)sizeof(int32_t), 256) : 0;
+    p->off_xd2 = off;     off += n_flag > 0 ? kb_round_up(nq * p->kp * (int64_t)sizeof(double), 256) : 0;
     p->total = off;
     return KB_OK;
 }
@@ -84,8 +86,7 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
     const int s = blockIdx.y;
     const int64_t t_lo = n_tiles * s / splits, t_hi = n_tiles * (s + 1) / splits;
 
-    KbRowList<KP, BM> list{ls, li};
-    float thr = __int_as_float(0x7f800000); int pos = 0;
+    KbRowList<KP, BM> list(ls, li);
     float my_len = 1.f;
     if (tid < BM) {
         list.init(tid);
@@ -134,7 +135,7 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
         if (tid < BM) {
             for (int c = 0; c < BN; ++c) {
                 const float sc = kb_score(tile[tid][c], colmeta[n0 + c], my_len);
-                if (sc < thr) list.insert(tid, sc, (int32_t)(n0 + c), thr, pos);
+                if (sc < list.bound) list.insert(tid, sc, (int32_t)(n0 + c));
             }
         }
         __syncthreads();
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(256)
 k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
                 const kb_rowmeta* __restrict__ rowmeta, int64_t q_row0, int64_t nq, int splits, int32_t k,
                 const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                const int32_t* __restrict__ extra_idx, const double* __restrict__ extra_d2,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist, double* __restrict__ out_d2) {
     constexpr int MAXC = 16;                                  // splits*KP <= 32*MAXC
     const int lane = threadIdx.x & 31;
@@ -191,9 +193,16 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
         }
         if (lane == r) my_idx = wi;
     }
-    // ---- 2. self must be a candidate: it replaces the last slot if it is missing
+    // ---- 2. exact-side-path extras (rows the tensor path cannot score exactly): lane e also
+    //         holds extra candidate e with its exact d2.  A flagged QUERY keeps only extras.
     const int32_t self = (int32_t)(q_row0 + q);
-    const unsigned has_self = __ballot_sync(0xffffffffu, my_idx == self);
+    int32_t x_idx = -1; double x_d2 = 0.0;
+    if (extra_idx) {
+        if (lane < KP) { x_idx = extra_idx[q * KP + lane]; x_d2 = extra_d2[q * KP + lane]; }
+        if (rowmeta[self].flags & 3) my_idx = -1;
+    }
+    // self must be a candidate: it replaces the last slot if it is missing
+    const unsigned has_self = __ballot_sync(0xffffffffu, my_idx == self || x_idx == self);
     if (!has_self && lane == KP - 1) my_idx = self;
     // ---- 3. exact distances: all lanes cooperate on one candidate at a time
     const __half* qrow = op + (int64_t)self * ld;
@@ -201,7 +210,7 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
     double my_d2 = 0.0;
     for (int e = 0; e < KP; ++e) {
         const int32_t j = __shfl_sync(0xffffffffu, my_idx, e);
-        if (j < 0) continue;
+        if (j < 0 || j == self) continue;                     // d2(self) = 0 exactly
         const __half* krow = op + (int64_t)j * ld;
         const double lj = (double)rowmeta[j].key_len;
         double acc = 0.0;
@@ -223,26 +232,157 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
         const double den = (lq * lj) * (lq * lj);
         if (lane == e) my_d2 = acc / den;
     }
-    // ---- 4. order: self first, then (d2, idx); rank by counting
-    const bool valid = (lane < KP) && (my_idx >= 0);
-    const double key_d = (my_idx == self) ? -1.0 : my_d2;
-    int rank = 0;
+    // ---- 4. order: self first, then (d2, idx); rank by counting over both item sets
+    const bool valid_a = (lane < KP) && (my_idx >= 0);
+    const bool valid_b = (lane < KP) && (x_idx >= 0);
+    const double key_a = (my_idx == self) ? -1.0 : my_d2;
+    const double key_b = (x_idx == self) ? -1.0 : x_d2;
+    int rank_a = 0, rank_b = 0;
     for (int e = 0; e < KP; ++e) {
         const int32_t oj = __shfl_sync(0xffffffffu, my_idx, e);
-        const double od = __shfl_sync(0xffffffffu, key_d, e);
-        if (oj >= 0 && e != lane && (od < key_d || (od == key_d && oj < my_idx))) ++rank;
+        const double od = __shfl_sync(0xffffffffu, key_a, e);
+        const int32_t xj = __shfl_sync(0xffffffffu, x_idx, e);
+        const double xd = __shfl_sync(0xffffffffu, key_b, e);
+        if (oj >= 0) {
+            if (e != lane && (od < key_a || (od == key_a && oj < my_idx))) ++rank_a;
+            if (od < key_b || (od == key_b && oj < x_idx)) ++rank_b;
+        }
+        if (xj >= 0) {
+            if (xd < key_a || (xd == key_a && xj < my_idx)) ++rank_a;
+            if (e != lane && (xd < key_b || (xd == key_b && xj < x_idx))) ++rank_b;
+        }
     }
-    if (valid && rank < k) {
-        out_idx[q * k + rank] = my_idx;
-        out_dist[q * k + rank] = (float)sqrt(my_d2);
-        if (out_d2) out_d2[q * k + rank] = my_d2;
+    if (valid_a && rank_a < k) {
+        out_idx[q * k + rank_a] = my_idx;
+        out_dist[q * k + rank_a] = (float)sqrt(my_d2);
+        if (out_d2) out_d2[q * k + rank_a] = my_d2;
     }
-    // fewer valid candidates than k (only when nk < KP and ... ) -> mark the rest
-    const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+    if (valid_b && rank_b < k) {
+        out_idx[q * k + rank_b] = x_idx;
+        out_dist[q * k + rank_b] = (float)sqrt(x_d2);
+        if (out_d2) out_d2[q * k + rank_b] = x_d2;
+    }
+    // fewer valid candidates than k -> mark the rest
+    const int n_valid = __popc(__ballot_sync(0xffffffffu, valid_a)) + __popc(__ballot_sync(0xffffffffu, valid_b));
     if (lane >= n_valid && lane < k) {
         out_idx[q * k + lane] = -1;
         out_dist[q * k + lane] = INF;
         if (out_d2) out_d2[q * k + lane] = (double)INF;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4x: exact side path.  Rows whose counts do not fit the tensor path exactly
+// (flags bit0: a count > 2048, bit1: sum c^2 >= 2^24 -- contigs beyond ~130 kb, long
+// homopolymers) are "flagged": masked out of the Gram kernel and handled here in fp64
+// from their true u32 counts.  One CTA per query row:
+//   flagged query   -> exact d2 to EVERY key
+//   unflagged query -> exact d2 to every FLAGGED key
+// and the KP best go to K5 as extra candidates.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int find_slot(const int32_t* __restrict__ rows, int n, int32_t row) {
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int32_t v = rows[mid];
+        if (v == row) return mid;
+        if (v < row) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256)
+k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta* __restrict__ rowmeta,
+          int64_t nk, int64_t q_row0, int64_t nq,
+          const int32_t* __restrict__ flag_rows, const uint32_t* __restrict__ flag_counts, int64_t ld_fc,
+          int32_t fc_cols, int32_t n_flag,
+          int32_t* __restrict__ extra_idx, double* __restrict__ extra_d2) {
+    extern __shared__ __align__(16) uint32_t qrow[];          // dp exact counts of the query row
+    __shared__ double wl_d[8][KP];
+    __shared__ int32_t wl_i[8][KP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double DINF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        const int32_t self = (int32_t)(q_row0 + q);
+        const kb_rowmeta mq = rowmeta[self];
+        const bool q_flagged = (mq.flags & 3) != 0;
+        __syncthreads();
+        if (q_flagged) {
+            const int slot = find_slot(flag_rows, n_flag, self);
+            for (int c = threadIdx.x; c < dp; c += 256)
+                qrow[c] = (slot >= 0 && c < fc_cols) ? flag_counts[(int64_t)slot * ld_fc + c] : 0u;
+        } else {
+            for (int c = threadIdx.x; c < dp; c += 256) qrow[c] = (uint32_t)__half2float(op[(int64_t)self * ld + c]);
+        }
+        if (lane < KP) { wl_d[warp][lane] = DINF; wl_i[warp][lane] = -1; }
+        if (KP > 32 && lane + 32 < KP) { wl_d[warp][lane + 32] = DINF; wl_i[warp][lane + 32] = -1; }
+        __syncthreads();
+        const double lq = (double)mq.key_len;
+        const int64_t n_keys = q_flagged ? nk : (int64_t)n_flag;
+        double thr = DINF; int pos = 0;                        // lane 0: worst entry of this warp's list
+        for (int64_t t = warp; t < n_keys; t += 8) {
+            const int32_t j = q_flagged ? (int32_t)t : flag_rows[t];
+            const kb_rowmeta mj = rowmeta[j];
+            if (mj.flags & 8) continue;                        // padding row of a multi-rank gather
+            const double lj = (double)mj.key_len;
+            double acc = 0.0;
+            if (mj.flags & 3) {
+                const int slot = find_slot(flag_rows, n_flag, j);
+                const uint32_t* krow = flag_counts + (int64_t)slot * ld_fc;
+                for (int c = lane; c < dp; c += 32) {
+                    const double b = (slot >= 0 && c < fc_cols) ? (double)krow[c] : 0.0;
+                    const double d = (double)qrow[c] * lj - b * lq;
+                    acc = fma(d, d, acc);
+                }
+            } else {
+                const __half* krow = op + (int64_t)j * ld;
+                for (int c = 2 * lane; c < dp; c += 64) {
+                    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(krow + c));
+                    const double d0 = (double)qrow[c] * lj - (double)fb.x * lq;
+                    const double d1 = (double)qrow[c + 1] * lj - (double)fb.y * lq;
+                    acc = fma(d0, d0, acc);
+                    acc = fma(d1, d1, acc);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const double d2 = acc / ((lq * lj) * (lq * lj));
+                if (d2 < thr || (d2 == thr && wl_i[warp][pos] < 0)) {
+                    wl_d[warp][pos] = d2; wl_i[warp][pos] = j;
+                    double m = -1.0; int mp = 0;
+                    for (int e = 0; e < KP; ++e) {
+                        const double x = wl_i[warp][e] < 0 ? DINF : wl_d[warp][e];
+                        if (x > m) { m = x; mp = e; }
+                    }
+                    thr = m; pos = mp;
+                }
+            }
+        }
+        __syncthreads();
+        // merge the 8 warp lists: KP rounds of arg-min over 8*KP entries by one warp
+        if (warp == 0) {
+            for (int r = 0; r < KP; ++r) {
+                double best = DINF; int32_t bi = 0x7fffffff; int bslot = -1;
+                for (int e = lane; e < 8 * KP; e += 32) {
+                    const int32_t ii = wl_i[e / KP][e % KP];
+                    const double dd = wl_d[e / KP][e % KP];
+                    if (ii >= 0 && (dd < best || (dd == best && ii < bi))) { best = dd; bi = ii; bslot = e; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+                    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; bslot = os; }
+                }
+                if (lane == 0) {
+                    extra_idx[q * KP + r] = (bslot >= 0) ? bi : -1;
+                    extra_d2[q * KP + r] = (bslot >= 0) ? best : DINF;
+                    if (bslot >= 0) wl_i[bslot / KP][bslot % KP] = -1;
+                }
+                __syncwarp();
+            }
+        }
     }
 }
 
@@ -261,12 +401,30 @@ int run_simt(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int3
 
 template <int KP>
 int run_rerank(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp,
-               const kb_rowmeta* rowmeta, int64_t q_row0, int64_t nq, int32_t k, uint8_t* ws,
+               const kb_rowmeta* rowmeta, int64_t q_row0, int64_t nq, int32_t k, uint8_t* ws, bool extras,
                int32_t* d_idx, float* d_dist, double* d_d2) {
     const int64_t grid = (nq + 7) / 8;
     k5_merge_rerank<KP><<<(unsigned)grid, 256, 0, ctx->stream>>>(
         op, ld, dp, rowmeta, q_row0, nq, p.splits, k, reinterpret_cast<const float*>(ws + p.off_score),
-        reinterpret_cast<const int32_t*>(ws + p.off_idx), d_idx, d_dist, d_d2);
+        reinterpret_cast<const int32_t*>(ws + p.off_idx),
+        extras ? reinterpret_cast<const int32_t*>(ws + p.off_xidx) : nullptr,
+        extras ? reinterpret_cast<const double*>(ws + p.off_xd2) : nullptr, d_idx, d_dist, d_d2);
+    ctx->launches++;
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+template <int KP>
+int run_exact(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp, const kb_rowmeta* rowmeta,
+              int64_t nk, int64_t q_row0, int64_t nq, const int32_t* flag_rows, const uint32_t* flag_counts,
+              int64_t ld_fc, int32_t fc_cols, int32_t n_flag, uint8_t* ws) {
+    auto kern = k4x_exact<KP>;
+    const size_t smem = (size_t)dp * sizeof(uint32_t);
+    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = nq < (int64_t)ctx->sm_count * 8 ? nq : (int64_t)ctx->sm_count * 8;
+    kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(op, ld, dp, rowmeta, nk, q_row0, nq, flag_rows, flag_counts, ld_fc,
+                                                     fc_cols, n_flag, reinterpret_cast<int32_t*>(ws + p.off_xidx),
+                                                     reinterpret_cast<double*>(ws + p.off_xd2));
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;
@@ -274,12 +432,12 @@ int run_rerank(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, in
 
 }  // namespace
 
-extern "C" int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl) {
+extern "C" int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl, int64_t n_flag) {
     KbKnnPlan p;
     int64_t best = 0;
     for (int im = KB_KNN_SIMT; im <= KB_KNN_TC; ++im) {
         if (impl != KB_KNN_AUTO && impl != im) continue;
-        int rc = kb_knn_plan(148, im, nq, nk, k, &p);
+        int rc = kb_knn_plan(148, im, nq, nk, k, n_flag, &p);
         if (rc) return rc;
         if (p.total > best) best = p.total;
     }
@@ -290,6 +448,8 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
                       const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
                       const kb_rowmeta* d_rowmeta,
                       int64_t nk, int64_t q_row0, int64_t nq,
+                      const int32_t* d_flag_rows, const uint32_t* d_flag_counts, int64_t ld_flag_counts,
+                      int32_t flag_cols, int64_t n_flag,
                       int32_t* d_idx, float* d_dist, double* d_d2,
                       void* d_workspace, int64_t workspace_bytes) {
     KB_CHECK_ARG(ctx && d_operand && d_rowmeta && d_idx && d_dist && d_workspace, "null pointer");
@@ -301,7 +461,9 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
     if (impl == KB_KNN_AUTO) impl = (nk >= 512) ? KB_KNN_TC : KB_KNN_SIMT;
     KB_CHECK_ARG(impl == KB_KNN_SIMT || impl == KB_KNN_TC, "impl");
     KbKnnPlan p;
-    int rc = kb_knn_plan(ctx->sm_count, impl, nq, nk, k, &p);
+    KB_CHECK_ARG(n_flag >= 0 && n_flag < (1LL << 31) && (n_flag == 0 || (d_flag_rows && d_flag_counts && ld_flag_counts >= flag_cols)),
+                 "flagged-row side inputs");
+    int rc = kb_knn_plan(ctx->sm_count, impl, nq, nk, k, n_flag, &p);
     if (rc) return rc;
     if (p.splits * p.kp > 32 * 16) { kb_set_error("internal: too many candidates per row"); return KB_EUNSUPPORTED; }
     if (workspace_bytes < p.total) { kb_set_error("kNN workspace: need %lld bytes, got %lld", (long long)p.total, (long long)workspace_bytes); return KB_EWORKSPACE; }
@@ -327,12 +489,22 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
         }
         if (rc) return rc;
     }
+    const bool extras = n_flag > 0;
+    if (extras) {
+        KbTimer t(ctx, 6);
+        switch (p.kp) {
+            case 8: rc = run_exact<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
+            case 16: rc = run_exact<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
+            default: rc = run_exact<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
+        }
+        if (rc) return rc;
+    }
     {
         KbTimer t(ctx, 5);
         switch (p.kp) {
-            case 8: rc = run_rerank<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
-            case 16: rc = run_rerank<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
-            default: rc = run_rerank<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, d_idx, d_dist, d_d2); break;
+            case 8: rc = run_rerank<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
+            case 16: rc = run_rerank<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
+            default: rc = run_rerank<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
         }
     }
     return rc;

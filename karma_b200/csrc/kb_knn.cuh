@@ -14,10 +14,10 @@ struct KbKnnPlan {
     int splits;          // S
     int64_t nk_pad;      // colmeta length (multiple of bn)
     // workspace offsets (bytes)
-    int64_t off_colmeta, off_score, off_idx, off_rowthr, total;
+    int64_t off_colmeta, off_score, off_idx, off_rowthr, off_xidx, off_xd2, total;
 };
 
-int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, KbKnnPlan* p);
+int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64_t n_flag, KbKnnPlan* p);
 
 // score of key j for query i, up to a per-row constant and positive factor:
 //   l_i * d2_ij - n_i/l_i = l_i * n_j/l_j^2 - 2 g_ij / l_j  =  fma(g, cm.x, l_i * cm.y)
@@ -27,25 +27,49 @@ __device__ __forceinline__ float kb_score(float g, float2 cm, float li) {
 }
 
 // Per-row running top-KP list in shared memory, entry e of row r at [e*ROWS + r]
-// (bank = r % 32: conflict-free for one thread per row).
+// (bank = r % 32: conflict-free for one thread per row).  The list is unsorted and
+// organised as KP/8 groups of 8 slots; the worst entry of every group (value + slot) is
+// cached in registers, so replacing the overall worst entry costs one 8-slot rescan
+// whatever KP is.  `bound` = the KP-th best score seen so far (+inf until the list is full).
 template <int KP, int ROWS>
 struct KbRowList {
+    static constexpr int NG = KP / 8;
+    static_assert(KP % 8 == 0 && NG >= 1 && NG <= 8, "KP must be a multiple of 8, at most 64");
     float* s; int32_t* i;
+    float gmax[NG]; int gpos[NG];
+    float bound;
+    __device__ __forceinline__ KbRowList(float* s_, int32_t* i_) : s(s_), i(i_), bound(0.f) {}
     __device__ __forceinline__ void init(int r) {
+        const float inf = __int_as_float(0x7f800000);
 #pragma unroll
-        for (int e = 0; e < KP; ++e) { s[e * ROWS + r] = __int_as_float(0x7f800000); i[e * ROWS + r] = -1; }
+        for (int e = 0; e < KP; ++e) { s[e * ROWS + r] = inf; i[e * ROWS + r] = -1; }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { gmax[g] = inf; gpos[g] = 0; }
+        bound = inf;
     }
-    // replace the current worst (at pos) and rescan for the new worst (cold path: an
-    // element beat the running bound).  thr/pos stay in registers.
-    __device__ __forceinline__ void insert(int r, float v, int32_t j, float& thr, int& pos) {
-        s[pos * ROWS + r] = v; i[pos * ROWS + r] = j;
-        float m = s[r]; int mp = 0;
-#pragma unroll 4
-        for (int e = 1; e < KP; ++e) {
-            const float x = s[e * ROWS + r];
+    // cold path: v beat the bound -> it replaces the current overall worst entry
+    __device__ __forceinline__ void insert(int r, float v, int32_t j) {
+        int gs = 0; float gm = gmax[0];
+#pragma unroll
+        for (int g = 1; g < NG; ++g) if (gmax[g] > gm) { gm = gmax[g]; gs = g; }
+        int ps = gpos[0];
+#pragma unroll
+        for (int g = 1; g < NG; ++g) if (g == gs) ps = gpos[g];
+        const int base = (gs * 8) * ROWS + r;
+        s[base + ps * ROWS] = v; i[base + ps * ROWS] = j;
+        float m = s[base]; int mp = 0;
+#pragma unroll
+        for (int e = 1; e < 8; ++e) {
+            const float x = s[base + e * ROWS];
             if (x > m) { m = x; mp = e; }
         }
-        thr = m; pos = mp;
+        float b = m;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if (g == gs) { gmax[g] = m; gpos[g] = mp; }
+            else b = fmaxf(b, gmax[g]);
+        }
+        bound = b;
     }
 };
 

@@ -22,6 +22,7 @@
 // Roofline: tensor pipe.  Algorithmic flops = 2 * nq * nk * D.
 #include "kb_knn.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -97,6 +98,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// multicast variants (cluster of 2 CTAs that share the B tile)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -133,10 +149,13 @@ struct TcParams {
 // every later unit of the same rows.
 struct Unit {
     int64_t mb; int s; int64_t t_lo, cnt, shift;
-    __device__ __forceinline__ Unit(const TcParams& p, int64_t u) {
-        mb = u % p.m_blocks;
-        const int s_run = (int)(u / p.m_blocks);
-        const int64_t td = (p.q_row0 + mb * BM) / BN;                 // diagonal tile of this block
+    // CL query blocks (one per CTA of the cluster) share a unit: same key tiles, same order
+    __device__ __forceinline__ Unit(const TcParams& p, int64_t u, int cl, int cta_rank) {
+        const int64_t groups = (p.m_blocks + cl - 1) / cl;
+        const int64_t grp = u % groups;
+        const int s_run = (int)(u / groups);
+        mb = grp * cl + cta_rank;
+        const int64_t td = (p.q_row0 + grp * cl * BM) / BN;           // diagonal tile of the group's first block
         int sd = (int)((td * p.splits) / p.n_tiles);
         while (sd + 1 < p.splits && (p.n_tiles * (sd + 1)) / p.splits <= td) ++sd;
         while (sd > 0 && (p.n_tiles * sd) / p.splits > td) --sd;
@@ -168,7 +187,10 @@ struct Smem {
     static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
 };
 
-template <int KP, int STAGES>
+// CL = 1: stand-alone CTAs.  CL = 2: clusters of two CTAs with adjacent query blocks; each
+// loads half of every B tile and TMA-multicasts it to both, which cuts the L2->SM operand
+// traffic per tile from 384 to 256 rows (the v2 profile had the L2 at 73 % of peak).
+template <int KP, int STAGES, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     using L = Smem<KP, STAGES>;
@@ -187,7 +209,9 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        // a stage is free again once the MMAs of EVERY CTA that receives multicast data into
+        // it have retired: each CTA's commit arrives on all CL empty barriers
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -199,17 +223,20 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();                // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t n_units = p.m_blocks * p.splits;
+    const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int64_t n_units = ((p.m_blocks + CL - 1) / CL) * p.splits;
+    const int64_t u0 = blockIdx.x / CL, ustep = gridDim.x / CL;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const Unit un(p, u);
+            for (int64_t u = u0; u < n_units; u += ustep) {
+                const Unit un(p, u, CL, cta_rank);
                 const int32_t arow = (int32_t)(p.q_row0 + un.mb * BM);
                 for (int64_t i = 0; i < un.cnt; ++i) {
                     const int32_t brow = (int32_t)(un.tile(i) * BN);
@@ -219,8 +246,13 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                         const uint32_t fb = bar_full + 8 * stage;
                         mbar_expect_tx(fb, STAGE_BYTES);
                         tma_load_2d(sa, &tmap, kb * BK, arow, fb);
-                        tma_load_2d(sa + A_BYTES, &tmap, kb * BK, brow, fb);
-                        tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, kb * BK, brow + 128, fb);
+                        if constexpr (CL == 1) {
+                            tma_load_2d(sa + A_BYTES, &tmap, kb * BK, brow, fb);
+                            tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, kb * BK, brow + 128, fb);
+                        } else {
+                            // my half of B goes to the same smem offset (and full barrier) of both CTAs
+                            tma_load_2d_mc(sa + A_BYTES + cta_rank * (B_BYTES / 2), &tmap, kb * BK, brow + 128 * cta_rank, fb, (uint16_t)0x3);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -231,8 +263,8 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const Unit un(p, u);
+            for (int64_t u = u0; u < n_units; u += ustep) {
+                const Unit un(p, u, CL, cta_rank);
                 for (int64_t i = 0; i < un.cnt; ++i) {
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
                     tc_fence_after();
@@ -248,7 +280,9 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                             // +32 B per K=16 step inside the 128 B swizzle atom (>>4 => +2)
                             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
                         }
-                        umma_commit(bar_empty + 8 * stage);          // frees the smem stage when the MMAs retire
+                        // frees the smem stage (here and in the peer CTA) when these MMAs retire
+                        if constexpr (CL == 1) umma_commit(bar_empty + 8 * stage);
+                        else umma_commit_mc(bar_empty + 8 * stage, (uint16_t)0x3);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(bar_tfull + 8 * acc);                // accumulator ready for the epilogue
@@ -261,19 +295,18 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
         const int r = quad * 32 + lane;                      // row of the 128-row tile
         const int et = threadIdx.x - 64;                     // 0..127
-        KbRowList<KP, BM> list{reinterpret_cast<float*>(smem + L::OFF_LIST_S),
-                               reinterpret_cast<int32_t*>(smem + L::OFF_LIST_I)};
+        KbRowList<KP, BM> list(reinterpret_cast<float*>(smem + L::OFF_LIST_S),
+                               reinterpret_cast<int32_t*>(smem + L::OFF_LIST_I));
         const float4* cm4 = reinterpret_cast<const float4*>(smem + L::OFF_COLMETA);
         float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const Unit un(p, u);
+        for (int64_t u = u0; u < n_units; u += ustep) {
+            const Unit un(p, u, CL, cta_rank);
             const int64_t q = un.mb * BM + r;
             const bool live = q < p.nq;
             const float li = live ? (float)p.rowmeta[p.q_row0 + q].key_len : 1.f;
             list.init(r);
             float thr = __int_as_float(0x7f800000);          // min(own KP-th best, row_thr): the prune bound
-            float own = thr; int pos = 0;                    // own list's worst entry and its slot
             for (int64_t i = 0; i < un.cnt; ++i) {
                 const int64_t n0 = un.tile(i) * BN;
                 // stage this tile's key metadata (all 128 epilogue threads); refresh the shared bound
@@ -309,8 +342,8 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
                             if (sc[x] < thr) {
-                                list.insert(r, sc[x], (int32_t)(n0 + c * 32 + x), own, pos);
-                                thr = fminf(thr, own);
+                                list.insert(r, sc[x], (int32_t)(n0 + c * 32 + x));
+                                thr = fminf(thr, list.bound);
                             }
                         }
                     }
@@ -320,7 +353,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 // publish a full list's bound for the other units of these rows
-                if (live && own < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(own));
+                if (live && list.bound < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(list.bound));
             }
             if (live) {
                 const int64_t base = (q * p.splits + un.s) * KP;
@@ -334,6 +367,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();                // no CTA leaves while its peer may still signal it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -344,16 +378,36 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int KP, int STAGES>
-int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int64_t n_units) {
+template <int KP, int STAGES, int CL>
+int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
     using L = Smem<KP, STAGES>;
-    auto kern = k4_tc<KP, STAGES>;
+    auto kern = k4_tc<KP, STAGES, CL>;
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    const int64_t grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
-    kern<<<(unsigned)grid, NUM_THREADS, L::TOTAL, ctx->stream>>>(tmap, prm);
+    const int64_t n_units = ((prm.m_blocks + CL - 1) / CL) * prm.splits;
+    int64_t clusters = ctx->sm_count / CL;
+    if (clusters > n_units) clusters = n_units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    KB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, prm));
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;
+}
+
+template <int KP>
+int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
+    // pairs of query blocks share B through multicast whenever there are at least two blocks
+    const char* force = getenv("KB_KNN_CLUSTER");
+    const int cl = force ? atoi(force) : (prm.m_blocks >= 2 ? 2 : 1);
+    if (cl == 2) return launch_tc<KP, 4, 2>(ctx, tmap, prm);
+    return launch_tc<KP, 4, 1>(ctx, tmap, prm);
 }
 
 }  // namespace
@@ -387,10 +441,9 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
     prm.cand_score = reinterpret_cast<float*>(ws + p.off_score);
     prm.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
     prm.row_thr = reinterpret_cast<int32_t*>(ws + p.off_rowthr);
-    const int64_t n_units = p.m_blocks * p.splits;
     switch (p.kp) {
-        case 8: return launch_tc<8, 4>(ctx, tmap, prm, n_units);
-        case 16: return launch_tc<16, 4>(ctx, tmap, prm, n_units);
-        default: return launch_tc<32, 4>(ctx, tmap, prm, n_units);
+        case 8: return launch_tc_kp<8>(ctx, tmap, prm);
+        case 16: return launch_tc_kp<16>(ctx, tmap, prm);
+        default: return launch_tc_kp<32>(ctx, tmap, prm);
     }
 }

@@ -98,7 +98,30 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
     }
 }
 
+// OR of the flags of rows [0, n) into one word (rows with bit3 = gather padding are skipped)
+__global__ void __launch_bounds__(256)
+k3_flags_or(const kb_rowmeta* __restrict__ rowmeta, int64_t n, uint32_t* __restrict__ out) {
+    uint32_t v = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t f = rowmeta[i].flags;
+        if (!(f & 8)) v |= (uint32_t)f;
+    }
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(out, v);
+}
+
 }  // namespace
+
+extern "C" int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t n, uint32_t* d_out) {
+    KB_CHECK_ARG(ctx && d_rowmeta && d_out && n >= 0, "null pointer");
+    KB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(uint32_t), ctx->stream));
+    if (n == 0) return KB_OK;
+    const int64_t blocks = (n + 255) / 256;
+    k3_flags_or<<<(unsigned)(blocks < 296 ? blocks : 296), 256, 0, ctx->stream>>>(d_rowmeta, n, d_out);
+    ctx->launches++;
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
 
 extern "C" int kb_compact(kb_ctx* ctx, const uint32_t* d_in, int64_t ld_in, int32_t d_cols_in,
                           const int32_t* d_colmap, int64_t n,

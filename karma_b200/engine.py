@@ -228,14 +228,14 @@ class Engine:
         return nl.value, ex.value
 
     # ---- K1x / K2: column dictionary ---------------------------------------------
-    def build_columns(self, mode, d_bases, d_offsets, n, counts, exotic, presence, group=None):
+    def build_columns(self, mode, d_bases, d_offsets, n, counts, exotic, presence, group=None, reduced=False):
         """kmer.py:146-179.  Returns (columns, counts') where columns is the sorted
         list of observed k-mer strings and counts' the (n, D') matrix in that order.
         One collective (MAX over the presence vector, which also carries the
         "non-ACGT window seen" flag) and one D2H copy."""
         self._bind_stream()
         names = mode_column_names(mode)
-        if group is not None:
+        if group is not None and not reduced:
             import torch.distributed as dist
             dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)
         pres_h = presence.cpu().numpy()
@@ -294,26 +294,32 @@ class Engine:
         if rows > n:
             if operand is not None:
                 operand[n:] = 0
-            rowmeta[n:] = torch.tensor([0, 0, 1, 3], dtype=torch.int32, device=self.device)
+            rowmeta[n:] = torch.tensor([0, 0, 1, 11], dtype=torch.int32, device=self.device)   # flags 1|2|8: padding
         check(self.lib.kb_normalise(self.ctx, ptr(counts), counts.stride(0), d_cols, ptr(d_key_len), n,
                                     ptr(profile) if want_profile else None, ldp,
                                     ptr(operand), dp, ptr(rowmeta)))
         return profile, operand, rowmeta
 
     # ---- K4 + K5 ---------------------------------------------------------------------
-    def knn(self, operand, rowmeta, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False):
+    def knn(self, operand, rowmeta, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False,
+            flag_rows=None, flag_counts=None):
+        """K4 (+K4x) + K5.  flag_rows (int32, ascending key rows) / flag_counts (u32 rows, same
+        order) describe the rows the tensor path cannot score exactly (kb_rowmeta flags 1|2)."""
         self._bind_stream()
         nk, dp = operand.shape
         nq = nk - q_row0 if nq is None else nq
-        need = check(self.lib.kb_knn_workspace_bytes(nq, nk, k, impl))
+        n_flag = 0 if flag_rows is None else int(flag_rows.numel())
+        need = check(self.lib.kb_knn_workspace_bytes(nq, nk, k, impl, n_flag))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
         dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         d2 = torch.empty((nq, k), dtype=torch.float64, device=self.device) if want_d2 else None
         check(self.lib.kb_knn(self.ctx, impl, k, ptr(operand), operand.stride(0), dp, ptr(rowmeta),
-                              nk, q_row0, nq, ptr(idx), ptr(dist), ptr(d2),
-                              ptr(self._ws), self._ws.numel()))
+                              nk, q_row0, nq,
+                              ptr(flag_rows) if n_flag else None, ptr(flag_counts) if n_flag else None,
+                              flag_counts.stride(0) if n_flag else 0, flag_counts.shape[1] if n_flag else 0, n_flag,
+                              ptr(idx), ptr(dist), ptr(d2), ptr(self._ws), self._ws.numel()))
         return idx, dist, d2
 
 
@@ -332,45 +338,96 @@ def all_gather_rows(t, group):
 
 def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
                 want_profile=True, group=None, rank=0, world=1, n_total=None, gather_lists=False, bufs=None,
-                on_profile=None):
+                on_profile=None, optimistic=True, row0=0):
     """The hot path on device-resident inputs: K1 -> column dictionary (-> K1x/K2) -> K3
-    [-> all-gather of the operand shards -> K4 -> K5].  Returns device tensors plus the
-    column list; nothing but the presence vector (and row flags) is copied to the host.
-    ``bufs``: optional dict of preallocated counts/exotic/presence tensors.
+    [-> all-gather of the operand shards -> K4 (-> K4x) -> K5].  Returns device tensors plus
+    the column list.
+
+    ``optimistic``: real assemblies contain every ACGT k-mer column, no non-ACGT bytes and no
+    row beyond the exact range of the tensor path, so the whole pass is enqueued without a
+    host round trip on that assumption; the presence vector and the row records are copied
+    back asynchronously and VALIDATED at the end (one synchronisation per pass).  If the
+    assumption fails the pass is redone on the general path (compaction, exotic keys, exact
+    side path).  ``bufs``: optional preallocated counts/exotic/presence tensors.
     ``on_profile(profile)`` is called as soon as K3 has been enqueued (to start its D2H)."""
     mode = mode_of(kmer_size)
     b = bufs or {}
-    counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
     faithful = mode == KB_MODE_5P6 or mode >= 16
-    if faithful:
-        columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence, group=group)
+    names = mode_column_names(mode)
+    counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
+    multi = group is not None and world > 1
+    if multi:
+        import torch.distributed as dist
+        dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)     # one D+1 word collective
+    h_pres = None
+    if optimistic:
+        h_pres = engine.host_buffer("presence", (len(names) + 1,), torch.int32, True)
+        h_pres.copy_(presence, non_blocking=True)
+        columns = names
+    elif faithful:
+        columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence,
+                                               group=group if multi else None, reduced=True)
     else:
         if int(presence[-1].item()):
             raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (some windows contain other bytes)")
-        columns = mode_column_names(mode)
+        columns = names
     d_cols = len(columns)
     if d_cols == 0:
-        raise ZeroRowError(0)
+        raise ZeroRowError(row0)
     if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
         counts = counts.contiguous()
-    per = None
-    if group is not None and world > 1:
-        per = shard_bounds(n_total, world, rank)[2]
+    per = shard_bounds(n_total, world, rank)[2] if multi else None
     profile, operand, rowmeta = engine.normalise(
         counts, d_cols, d_key_len, want_profile=want_profile, want_operand=n_neighbors is not None, rows_alloc=per)
     if on_profile is not None and profile is not None:
         on_profile(profile)
     out = {"columns": columns, "d_cols": d_cols, "counts": counts, "profile": profile, "operand": operand,
            "rowmeta": rowmeta, "idx": None, "dist": None}
-    if n_neighbors is None:
-        return out
-    if per is not None:
+    all_op, all_meta = operand, rowmeta
+    if n_neighbors is not None and multi:
         # the one exchange step: every rank needs all keys -- two collectives, the fp16
         # operand shards and the 16-byte row records
         all_op = all_gather_rows(operand, group)
         all_meta = all_gather_rows(rowmeta, group)
-        idx, dst, _ = engine.knn(all_op, all_meta, n_neighbors, q_row0=rank * per, nq=n, impl=impl)
-        if gather_lists:
+    n_real = n_total if multi else n                    # padded index == global row: real rows are [0, n_real)
+    # one word summarises every row record (OR of the flags): that is all the host reads back
+    d_or = torch.empty(1, dtype=torch.int32, device=engine.device)
+    check(engine.lib.kb_rowmeta_flags_or(engine.ctx, ptr(all_meta), all_meta.shape[0], ptr(d_or)))
+    h_or = engine.host_buffer("flags_or", (1,), torch.int32, True)
+    h_or.copy_(d_or, non_blocking=True)
+
+    def flags_host():
+        """Per-row flags (general path only: the optimistic path reads just the OR word)."""
+        return all_meta[:n_real, 3].cpu().numpy()
+
+    if n_neighbors is not None:
+        flag_rows = flag_counts = None
+        ids = []
+        if not optimistic:
+            torch.cuda.current_stream(engine.device).synchronize()
+            if int(h_or.numpy()[0]) & 3:                 # some row is beyond the exact range of the tensor path
+                ids = np.flatnonzero((flags_host() & 3) != 0).astype(np.int32)
+            if len(ids):
+                # true u32 count rows of the flagged contigs, in ascending global order
+                lo = rank * per if multi else 0
+                mine = ids[(ids >= lo) & (ids < lo + n)] - lo
+                local = counts[torch.from_numpy(mine.astype(np.int64)).to(engine.device)][:, :d_cols].contiguous() \
+                    if len(mine) else torch.zeros((0, d_cols), dtype=torch.int32, device=engine.device)
+                if multi:
+                    import torch.distributed as dist
+                    fmax = max(int(((ids >= r * per) & (ids < (r + 1) * per)).sum()) for r in range(world))
+                    pad = torch.zeros((fmax, d_cols), dtype=torch.int32, device=engine.device)
+                    pad[:len(mine)] = local
+                    allc = all_gather_rows(pad, group)
+                    keep = np.concatenate([r * fmax + np.arange(int(((ids >= r * per) & (ids < (r + 1) * per)).sum()))
+                                           for r in range(world)]).astype(np.int64)
+                    flag_counts = allc[torch.from_numpy(keep).to(engine.device)].contiguous()
+                else:
+                    flag_counts = local
+                flag_rows = torch.from_numpy(ids).to(engine.device)
+        idx, dst, _ = engine.knn(all_op, all_meta, n_neighbors, q_row0=(rank * per if multi else 0), nq=n, impl=impl,
+                                 flag_rows=flag_rows, flag_counts=flag_counts)
+        if multi and gather_lists:
             # k-lists back to every rank: [idx | dist bits] packed per row, one collective
             packed = torch.empty((per, 2 * n_neighbors), dtype=torch.int32, device=engine.device)
             if per > n:
@@ -379,10 +436,33 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
             packed[:n, n_neighbors:] = dst.view(torch.int32)
             g = all_gather_rows(packed, group)
             out.update(all_idx=g[:, :n_neighbors], all_dist=g[:, n_neighbors:].view(torch.float32))
-        out.update(all_rowmeta=all_meta)
-    else:
-        idx, dst, _ = engine.knn(operand, rowmeta, n_neighbors, impl=impl)
-    out.update(idx=idx, dist=dst)
+        out.update(idx=idx, dist=dst)
+
+    # ---- validation (the only host synchronisation of an optimistic pass)
+    torch.cuda.current_stream(engine.device).synchronize()
+    flags_or = int(h_or.numpy()[0])
+    if optimistic:
+        pres = h_pres.numpy()
+        redo = False
+        if pres[-1] != 0:
+            if not faithful:
+                raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (some windows contain other bytes)")
+            redo = True
+        if faithful and not pres[:-1].all():
+            redo = True
+        if n_neighbors is not None and (flags_or & 3):
+            redo = True
+        if redo:
+            return device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors, impl, want_profile,
+                               group, rank, world, n_total, gather_lists, bufs, on_profile, optimistic=False, row0=row0)
+    if flags_or & 4:
+        # a contig shorter than k (kmer.py:250-258): report the first such row of this rank
+        own = rowmeta[:n, 3].cpu().numpy()
+        zero = np.flatnonzero(own & 4)
+        if len(zero):
+            raise ZeroRowError(int(zero[0]) + row0)
+        if multi:
+            raise ZeroRowError(-1)                       # the all-zero row lives on another rank
     return out
 
 
@@ -420,22 +500,10 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
 
     r = device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors=n_neighbors, impl=impl,
                     want_profile=want_profile, group=group, rank=rank, world=world, n_total=n_total,
-                    on_profile=start_download if want_profile else None)
-    gathered = "all_rowmeta" in r
-    flags = r["all_rowmeta" if gathered else "rowmeta"][:, 3].cpu().numpy()
-    own = r["rowmeta"][:n, 3].cpu().numpy() if gathered else flags[:n]
-    zero = np.flatnonzero(own & 4)
-    if len(zero):
-        torch.cuda.synchronize(engine.device)
-        raise ZeroRowError(int(zero[0]) + row0)
+                    on_profile=start_download if want_profile else None, row0=row0)
     out = {"columns": r["columns"], "profile": None, "knn_idx": None, "knn_dist": None,
            "d_profile": r["profile"], "d_operand": r["operand"]}
     if n_neighbors is not None:
-        # padded index == global row, so the real rows of the gathered set are [0, n_total)
-        real = np.arange(len(flags)) < (n_total if gathered else len(flags))
-        if ((flags & 3) != 0)[real].any():
-            torch.cuda.synchronize(engine.device)
-            raise _lib.KarmaB200Error(-6, "a k-mer count > 2048 or a squared norm >= 2^24 needs the exact side path (not built yet)")
         h_idx = engine.host_buffer("knn_idx", tuple(r["idx"].shape), torch.int32, reuse_host)
         h_dst = engine.host_buffer("knn_dist", tuple(r["dist"].shape), torch.float32, reuse_host)
         h_idx.copy_(r["idx"], non_blocking=True)

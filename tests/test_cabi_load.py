@@ -45,9 +45,9 @@ def test_pure_host_entry_points(lib):
     assert lib.kb_mode_columns(_lib.KB_MODE_DENSE_4_5) == 1280
     assert [lib.kb_mode_columns(_lib.KB_MODE_K(k)) for k in range(1, 8)] == [4 ** k for k in range(1, 8)]
     assert lib.kb_mode_columns(999) < 0 and b"unknown column mode" in lib.kb_last_error()
-    assert lib.kb_knn_workspace_bytes(1000, 1000, 2, 0) > 0
-    assert lib.kb_knn_workspace_bytes(1000, 1000, 200, 0) < 0          # unsupported k is an error, not a fallback
-    assert lib.kb_knn_workspace_bytes(10, 5, 8, 0) < 0                  # k > nk
+    assert lib.kb_knn_workspace_bytes(1000, 1000, 2, 0, 0) > 0
+    assert lib.kb_knn_workspace_bytes(1000, 1000, 200, 0, 0) < 0          # unsupported k is an error, not a fallback
+    assert lib.kb_knn_workspace_bytes(10, 5, 8, 0, 0) < 0                  # k > nk
 
 
 def test_no_cpu_fallback(lib):

@@ -112,3 +112,38 @@ def test_full_size_knn_properties_50k(engine):
     rows = np.arange(0, 50000, 1499)
     rep = knn_oracle.check_knn(idx[rows], dist[rows], knn_oracle.d2_fp64(prof, rows), rows=rows)
     assert knn_oracle.parity_ok(rep), rep
+
+
+def _assembly_from(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    bases = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8).copy()
+    n = len(seqs)
+    return synth.Assembly(bases, off, np.arange(n, dtype=np.int64) // 3, np.arange(n, dtype=np.int64) % 3 + 1)
+
+
+@pytest.mark.parametrize("k", [2, 6])
+def test_exact_side_path_for_rows_beyond_the_tensor_range(engine, k):
+    """Rows with a k-mer count > 2048 (long homopolymers) or sum c^2 >= 2^24 (contigs beyond
+    ~130 kb) cannot be scored exactly by the fp16/fp32 Gram; they take the fp64 side path
+    (K4x) as queries AND as keys of ordinary rows.  Result must still satisfy the tie rule."""
+    rng = np.random.default_rng(17)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    base = synth.s1_families(240, seed=9).as_dict()
+    seqs = list(base.values())
+    long_a = rnd(150000)
+    seqs += [long_a, long_a[:140000] + rnd(500), rnd(200000), "A" * 3000, "A" * 2990 + rnd(40), rnd(300) + "A" * 2500,
+             "ACGT" * 2200]
+    asm = _assembly_from(seqs)
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, "5p6")
+    assert (counts.max(1) > 2048).sum() >= 3 and ((counts.astype(np.int64) ** 2).sum(1) >= 2 ** 24).sum() >= 3
+    res = _run(engine, asm, "5p6", k, "tc")
+    prof = counts[:, counts.any(0)] / asm.key_len[:, None].astype(np.float64)
+    assert res["profile"].tobytes() == prof.tobytes()
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+    # the two near-identical long contigs must find each other
+    assert res["knn_idx"][240, 1] == 241 and res["knn_idx"][241, 1] == 240
