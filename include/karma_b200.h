@@ -196,6 +196,21 @@ KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
            int32_t* d_idx, float* d_dist, double* d_d2,
            void* d_workspace, int64_t workspace_bytes);
 
+/* ---- FASTA reader / packer (host only) --------------------------------------------
+ * Replaces read_fasta_file (karma.py:40-61) and the dict -> buffer marshalling: same
+ * record rules (first line is a header, key = first space-delimited token INCLUDING
+ * '>', universal newlines, line endings stripped from sequence lines, the last record
+ * always emitted).  kb_fasta_open reads and sizes the file; kb_fasta_fill writes
+ *  h_bases uint8[total_bases], h_offsets int64[n+1], h_key_len int32[n],
+ *  h_keys uint8[total_key_bytes] (keys back to back), h_key_offsets int64[n+1]
+ * (h_bases / h_keys / h_key_offsets may be NULL).  Non-ASCII files are rejected. */
+typedef struct kb_fasta kb_fasta;
+KB_API int kb_fasta_open(const char* path, kb_fasta** out, int64_t* n_records, int64_t* total_bases,
+                  int64_t* total_key_bytes);
+KB_API int kb_fasta_fill(kb_fasta* f, uint8_t* h_bases, int64_t* h_offsets, int32_t* h_key_len,
+                  uint8_t* h_keys, int64_t* h_key_offsets);
+KB_API int kb_fasta_close(kb_fasta* f);
+
 /* Per-stage device times.  With timing enabled every launch of a stage is bracketed
  * by a CUDA-event pair on the context stream (a ring of 128 pairs per stage).
  * kb_stage_ms synchronises, returns the mean duration (ms) and the number of launches

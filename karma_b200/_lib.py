@@ -50,6 +50,9 @@ SIGNATURES = {
     "kb_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32, c_int, c_int64]),
     "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int64,
                        _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64]),
+    "kb_fasta_open": (c_int, [c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "kb_fasta_fill": (c_int, [_P, _P, _P, _P, _P, _P]),
+    "kb_fasta_close": (c_int, [_P]),
     "kb_enable_timing": (c_int, [_P, c_int]),
     "kb_stage_ms": (c_int, [_P, c_int, POINTER(c_float), POINTER(c_int)]),
     "kb_launch_count": (c_int64, [_P]),

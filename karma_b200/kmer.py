@@ -113,6 +113,11 @@ class KmerClustering:
     def _pack(self):
         """dict -> packed buffers of the C ABI.  One byte per character (latin-1):
         byte order then equals the code-point order ``sorted()`` uses (kmer.py:172)."""
+        packed = getattr(self.sequences, "packed", None)
+        if callable(packed):
+            got = packed()                     # came from karma_b200.fasta.read_fasta_file, unmodified
+            if got is not None:
+                return got
         seqs = list(self.sequences.values())
         try:
             raw = "".join(seqs).encode("latin-1")
