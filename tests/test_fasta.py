@@ -83,6 +83,6 @@ def test_non_ascii_is_rejected(tmp_path):
     from karma_b200 import _lib
     path = tmp_path / "x.fa"
     with open(path, "wb") as f:
-        f.write(">a\nAC\xc3\xa9\n")
+        f.write(b">a\nAC\xc3\xa9\n")
     with pytest.raises(_lib.KarmaB200Error):
         fasta.read_fasta_file(path)
