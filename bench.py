@@ -59,6 +59,29 @@ def workload_name(a):
         a.contigs, a.synth, a.kmer, a.neighbors)
 
 
+def ncu_traffic(kernel_regex):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
+    committed `ncu --set full` summary of the same bench command (profiles/): None if absent."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "ncu_k4_*summary.csv"))):
+        rd = wr = None
+        name_ok = False
+        for line in open(path):
+            parts = line.rstrip("\n").split(",")
+            if parts[0] == "Kernel Name" and re.search(kernel_regex, line):
+                name_ok = True
+            if parts[0] == "dram__bytes_read.sum":
+                rd = (float(parts[-1]), parts[-2])
+            if parts[0] == "dram__bytes_write.sum":
+                wr = (float(parts[-1]), parts[-2])
+        if rd and wr:
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            best = {"bytes": rd[0] * scale.get(rd[1], 1.0) + wr[0] * scale.get(wr[1], 1.0), "source": os.path.relpath(path, ROOT)}
+    return best
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -353,7 +376,8 @@ def run_ours(a):
         "stage_ms": {"count": count_ms, "normalise": norm_ms, "knn_gemm": gemm_ms, "rerank": rerank_ms},
         "roofline": {"bound": "tensor", "kernel": "k4_tc (distance GEMM + fused top-k)" if a.knn_impl == "tc" else "k4_simt",
                      "achieved": ach_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["tflops"],
-                     "traffic": None, "peak_source": pk["source"] + ", bf16 burst; sustained %s" % pk["tflops_sustained"],
+                     "traffic": (ncu_traffic("k4_tc") or {}).get("bytes"), "traffic_source": (ncu_traffic("k4_tc") or {}).get("source"),
+                     "peak_source": pk["source"] + ", bf16 burst; sustained %s" % pk["tflops_sustained"],
                      "flops_per_launch": flops},
         "roofline_count": {"bound": "hbm", "kernel": "k1_count", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": ach_gbs / pk["hbm_gbs"], "bytes_per_launch": count_bytes},

@@ -204,16 +204,21 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
     // self must be a candidate: it replaces the last slot if it is missing
     const unsigned has_self = __ballot_sync(0xffffffffu, my_idx == self || x_idx == self);
     if (!has_self && lane == KP - 1) my_idx = self;
-    // ---- 3. exact distances: all lanes cooperate on one candidate at a time
+    // ---- 3. exact distances: all lanes cooperate on one candidate at a time.
+    //   sum_c (a_c*lj - b_c*lq)^2 = lj^2*n_q + lq^2*n_j - 2*lj*lq*g,  g = sum_c a_c*b_c.
+    //   Rows that reach this point are unflagged: counts <= 2048 and n < 2^24, hence
+    //   g <= sqrt(n_q*n_j) < 2^24 and every partial sum of the fp32 dot product is an
+    //   exactly representable integer -- the fp32 FMA chain IS the exact integer Gram entry.
+    //   The three terms are exact integers in fp64 (< 2^53), so d2 has one rounding (the division).
     const __half* qrow = op + (int64_t)self * ld;
-    const double lq = (double)rowmeta[self].key_len;
+    const kb_rowmeta mq = rowmeta[self];
+    const double lq = (double)mq.key_len;
     double my_d2 = 0.0;
     for (int e = 0; e < KP; ++e) {
         const int32_t j = __shfl_sync(0xffffffffu, my_idx, e);
         if (j < 0 || j == self) continue;                     // d2(self) = 0 exactly
         const __half* krow = op + (int64_t)j * ld;
-        const double lj = (double)rowmeta[j].key_len;
-        double acc = 0.0;
+        float g0 = 0.f, g1 = 0.f;
         for (int c = 8 * lane; c < dp; c += 256) {
             const uint4 a = *reinterpret_cast<const uint4*>(qrow + c);
             const uint4 b = *reinterpret_cast<const uint4*>(krow + c);
@@ -222,15 +227,18 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const float2 fa = __half22float2(ha[x]), fb = __half22float2(hb[x]);
-                const double t0 = (double)fa.x * lj - (double)fb.x * lq;
-                const double t1 = (double)fa.y * lj - (double)fb.y * lq;
-                acc = fma(t0, t0, acc);
-                acc = fma(t1, t1, acc);
+                g0 = fmaf(fa.x, fb.x, g0);
+                g1 = fmaf(fa.y, fb.y, g1);
             }
         }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const double den = (lq * lj) * (lq * lj);
-        if (lane == e) my_d2 = acc / den;
+        float g = g0 + g1;
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == e) {
+            const kb_rowmeta mj = rowmeta[j];
+            const double lj = (double)mj.key_len;
+            const double num = lj * lj * mq.sqnorm + lq * lq * mj.sqnorm - 2.0 * (lj * lq) * (double)g;
+            my_d2 = num / ((lq * lj) * (lq * lj));
+        }
     }
     // ---- 4. order: self first, then (d2, idx); rank by counting over both item sets
     const bool valid_a = (lane < KP) && (my_idx >= 0);

@@ -359,10 +359,7 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
     if multi:
         import torch.distributed as dist
         dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)     # one D+1 word collective
-    h_pres = None
     if optimistic:
-        h_pres = engine.host_buffer("presence", (len(names) + 1,), torch.int32, True)
-        h_pres.copy_(presence, non_blocking=True)
         columns = names
     elif faithful:
         columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence,
@@ -394,7 +391,15 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
     d_or = torch.empty(1, dtype=torch.int32, device=engine.device)
     check(engine.lib.kb_rowmeta_flags_or(engine.ctx, ptr(all_meta), all_meta.shape[0], ptr(d_or)))
     h_or = engine.host_buffer("flags_or", (1,), torch.int32, True)
-    h_or.copy_(d_or, non_blocking=True)
+    h_pres = engine.host_buffer("presence", (len(names) + 1,), torch.int32, True)
+
+    def fetch_validation_words():
+        # Small D2H copies are issued only where the stream has nothing left to launch behind
+        # them: a copy queued between K3 and K4 would sit behind the 0.4 GB profile transfer on
+        # the D2H copy engine and stall the kNN kernels of this stream.
+        h_or.copy_(d_or, non_blocking=True)
+        h_pres.copy_(presence, non_blocking=True)
+        torch.cuda.current_stream(engine.device).synchronize()
 
     def flags_host():
         """Per-row flags (general path only: the optimistic path reads just the OR word)."""
@@ -404,7 +409,7 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
         flag_rows = flag_counts = None
         ids = []
         if not optimistic:
-            torch.cuda.current_stream(engine.device).synchronize()
+            fetch_validation_words()
             if int(h_or.numpy()[0]) & 3:                 # some row is beyond the exact range of the tensor path
                 ids = np.flatnonzero((flags_host() & 3) != 0).astype(np.int32)
             if len(ids):
@@ -439,7 +444,7 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
         out.update(idx=idx, dist=dst)
 
     # ---- validation (the only host synchronisation of an optimistic pass)
-    torch.cuda.current_stream(engine.device).synchronize()
+    fetch_validation_words()
     flags_or = int(h_or.numpy()[0])
     if optimistic:
         pres = h_pres.numpy()

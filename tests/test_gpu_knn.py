@@ -147,3 +147,15 @@ def test_exact_side_path_for_rows_beyond_the_tensor_range(engine, k):
     assert knn_oracle.parity_ok(rep), rep
     # the two near-identical long contigs must find each other
     assert res["knn_idx"][240, 1] == 241 and res["knn_idx"][241, 1] == 240
+
+
+def test_dense_5120_k15_at_scale(engine):
+    """BASELINE configs 3/4 shape on one GPU at reduced N: 5120 dense columns, n_neighbors=15."""
+    asm = synth.s2_redundant(12000, seed=3)
+    res = _run(engine, asm, "5+6", 15, "tc")
+    idx, dist = res["knn_idx"], res["knn_dist"]
+    assert idx.shape == (12000, 15) and (idx[:, 0] == np.arange(12000)).all() and (dist[:, 0] == 0).all()
+    assert all(len(set(r)) == 15 for r in idx[::97].tolist()) and (np.diff(dist[:, 1:], axis=1) >= 0).all()
+    rows = np.arange(0, 12000, 401)
+    rep = knn_oracle.check_knn(idx[rows], dist[rows], knn_oracle.d2_fp64(res["profile"], rows), rows=rows)
+    assert knn_oracle.parity_ok(rep), rep
