@@ -92,7 +92,10 @@ __device__ __forceinline__ uint32_t accumulate_warp(const uint8_t* __restrict__ 
         const uint64_t codes = ((uint64_t)own << 16) | (uint64_t)halo;
         // non-ACGT bytes are rare: the per-base bad mask is only built when some lane saw one
         uint32_t bad = 0;                                                // base j at bit 23-j
-        if (__any_sync(FULL, ((x0 | x1 | x2 | x3 | y0 | y1) != 0) && A < end_abs)) {
+        // (the halo only counts when it was loaded: a contig's last vector has none)
+        const bool inv_own = ((x0 | x1 | x2 | x3) != 0) && A < end_abs;
+        const bool inv_halo = ((y0 | y1) != 0) && A + 16 < end_abs;
+        if (__any_sync(FULL, inv_own || inv_halo)) {
             bad = (badbits4(x0) << 20) | (badbits4(x1) << 16) | (badbits4(x2) << 12) | (badbits4(x3) << 8) |
                   (badbits4(y0) << 4) | badbits4(y1);
         }

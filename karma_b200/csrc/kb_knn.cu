@@ -12,6 +12,7 @@
 //     d2_ij = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2       (fp64, integer terms)
 #include "kb_knn.cuh"
 #include <math.h>
+#include <cstdlib>
 
 int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64_t n_flag, KbKnnPlan* p) {
     if (k < 1 || nq < 1 || nk < 1 || k > nk) { kb_set_error("kNN: need 1 <= k <= nk and nq >= 1"); return KB_EINVAL; }
@@ -26,6 +27,10 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64
     if (want > 16) want = 16;
     if (want > p->n_tiles) want = p->n_tiles;
     if (want < 1) want = 1;
+    if (const char* f = getenv("KB_KNN_SPLITS")) {              // experiments only
+        const int64_t v = atoll(f);
+        if (v >= 1) want = v < p->n_tiles ? v : p->n_tiles;
+    }
     p->splits = (int)want;
     p->nk_pad = p->n_tiles * p->bn;
     int64_t off = 0;

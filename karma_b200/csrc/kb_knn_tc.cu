@@ -129,6 +129,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+#ifdef KB_TC_STATS
+__device__ unsigned long long g_tc_inserts, g_tc_cold_chunks, g_tc_chunks;
+#endif
+
 struct TcParams {
     int64_t nk, q_row0, nq;
     int64_t m_blocks, n_tiles;
@@ -337,6 +341,10 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                         m0 = fminf(m0, sc[x]); m1 = fminf(m1, sc[x + 1]);
                         m2 = fminf(m2, sc[x + 2]); m3 = fminf(m3, sc[x + 3]);
                     }
+#ifdef KB_TC_STATS
+                    if (lane == 0) atomicAdd(&g_tc_chunks, 1ull);
+                    if (__any_sync(0xffffffffu, fminf(fminf(m0, m1), fminf(m2, m3)) < thr) && lane == 0) atomicAdd(&g_tc_cold_chunks, 1ull);
+#endif
                     if (fminf(fminf(m0, m1), fminf(m2, m3)) < thr) {
                         // cold path: some element of this chunk beats the bound
 #pragma unroll
@@ -344,6 +352,9 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                             if (sc[x] < thr) {
                                 list.insert(r, sc[x], (int32_t)(n0 + c * 32 + x));
                                 thr = fminf(thr, list.bound);
+#ifdef KB_TC_STATS
+                                atomicAdd(&g_tc_inserts, 1ull);
+#endif
                             }
                         }
                     }
@@ -411,6 +422,16 @@ int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
 }
 
 }  // namespace
+
+#ifdef KB_TC_STATS
+extern "C" __attribute__((visibility("default"))) int kb_debug_tc_stats(unsigned long long* out3, int reset) {
+    unsigned long long z = 0;
+    cudaMemcpyFromSymbol(&out3[0], g_tc_inserts, 8); cudaMemcpyFromSymbol(&out3[1], g_tc_cold_chunks, 8);
+    cudaMemcpyFromSymbol(&out3[2], g_tc_chunks, 8);
+    if (reset) { cudaMemcpyToSymbol(g_tc_inserts, &z, 8); cudaMemcpyToSymbol(g_tc_cold_chunks, &z, 8); cudaMemcpyToSymbol(g_tc_chunks, &z, 8); }
+    return 0;
+}
+#endif
 
 int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int64_t ld_operand,
                      int32_t d_cols_padded, const kb_rowmeta* d_rowmeta, int64_t nk, int64_t q_row0,
