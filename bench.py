@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--knn-impl", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard-gen", action="store_true", help="each rank synthesises only its own row shard")
     return ap.parse_args()
 
 
@@ -269,12 +270,20 @@ def run_ours(a):
     impl = _lib.KB_KNN_TC if a.knn_impl == "tc" else _lib.KB_KNN_SIMT
     k = a.neighbors
 
-    asm = synth.make(a.synth, a.contigs)
-    n_total = asm.n
+    n_total = a.contigs
     lo, hi, per = shard_bounds(n_total, world, rank)
-    shard = asm.slice(lo, hi) if world > 1 else asm
+    if world > 1 and (a.shard_gen or n_total >= 400000):
+        # large assemblies: every rank synthesises only its own rows (seeded per rank)
+        shard = synth.make(a.synth, hi - lo, seed=4321 + rank)
+        asm = None
+        tb = torch.tensor([int(shard.offsets[-1])], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tb)
+        total_bases_all = int(tb.item())
+    else:
+        asm = synth.make(a.synth, a.contigs)
+        shard = asm.slice(lo, hi) if world > 1 else asm
+        total_bases_all = int(asm.offsets[-1])
     n = shard.n
-    total_bases_all = int(asm.offsets[-1])
     h_bases = torch.from_numpy(shard.bases.copy()).pin_memory()
     h_offsets = torch.from_numpy(shard.offsets.copy()).pin_memory()
     h_keylen = torch.from_numpy(shard.key_len.copy()).pin_memory()
@@ -384,7 +393,7 @@ def run_ours(a):
     }
     if e2e:
         line["e2e"] = e2e
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and asm is not None:
         v, cores, sample, _ = cpu_arm(a, asm, 1, 0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))
