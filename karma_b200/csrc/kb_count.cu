@@ -24,8 +24,10 @@
 // Roofline: HBM.  Algorithmic bytes per contig = L (bases) + 4*cols (row).
 #include "kb_common.cuh"
 
-#define KB_LONG_THRESHOLD (1 << 16)   // bases; longer contigs take the split path
-#define KB_LONG_CHUNK     (1 << 14)   // window starts per CTA work item (split path)
+// Contigs longer than `long_threshold` bases take the split path, `long_chunk` window starts per CTA
+// work item.  Large inputs: 64 kb / 16 kb.  Small inputs (fewer contigs than resident warps, e.g. one
+// rank's shard of a strong-scaled run): 4 kb / 4 kb, so that one 15 kb contig does not become the tail.
+struct LongPolicy { int64_t threshold, chunk; };
 
 namespace {
 
@@ -209,7 +211,7 @@ template <int KA, int KB, bool PALB, bool PERMUTE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
               uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
+              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm, LongPolicy lp) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     extern __shared__ __align__(16) uint32_t smem_hist[];
     const int lane = threadIdx.x & 31;
@@ -225,7 +227,7 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
         const int64_t beg = offsets[row];
         const int64_t L = offsets[row + 1] - beg;
         uint32_t* out = counts + row * ld;
-        if (L > KB_LONG_THRESHOLD) {
+        if (L > lp.threshold) {
             // queue for the split kernel; zero the row it will red.add into
             if (lane == 0) {
                 const int slot = atomicAdd(&scratch[1], 1);
@@ -256,7 +258,7 @@ template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
              uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-             uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
+             uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm, LongPolicy lp) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     extern __shared__ __align__(16) uint32_t hist[];
     __shared__ uint32_t s_red[THREADS / 32];
@@ -273,7 +275,7 @@ k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offs
         const int64_t beg = offsets[row];
         const int64_t L = offsets[row + 1] - beg;
         uint32_t* out = counts + row * ld;
-        if (L > KB_LONG_THRESHOLD) {
+        if (L > lp.threshold) {
             if (threadIdx.x == 0) {
                 const int slot = atomicAdd(&scratch[1], 1);
                 scratch[4 + slot] = (int32_t)row;
@@ -305,7 +307,7 @@ template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets,
               uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm) {
+              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm, LongPolicy lp) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     extern __shared__ __align__(16) uint32_t hist[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,10 +319,10 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
         const int64_t row = scratch[4 + li];
         const int64_t beg = offsets[row];
         const int64_t L = offsets[row + 1] - beg;
-        const int64_t n_chunks = (L + KB_LONG_CHUNK - 1) / KB_LONG_CHUNK;
+        const int64_t n_chunks = (L + lp.chunk - 1) / lp.chunk;
         for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-            const int64_t lo = c * KB_LONG_CHUNK;
-            const int64_t hi = (lo + KB_LONG_CHUNK < L) ? lo + KB_LONG_CHUNK : L;
+            const int64_t lo = c * lp.chunk;
+            const int64_t hi = (lo + lp.chunk < L) ? lo + lp.chunk : L;
             const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB>(bases, beg, L, lo, hi, hist, hist + COLS + threadIdx.x,
                                                                       ((beg + lo) & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
             if (lane == 0 && ex) {
@@ -362,6 +364,7 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
     }
     KB_CUDA(cudaMemsetAsync(ctx->d_k1_scratch, 0, 4 * sizeof(int32_t), ctx->stream));
     const size_t smem_one = (size_t)(COLS + THREADS) * sizeof(uint32_t);   // histogram + dummy words
+    LongPolicy lp{1 << 16, 1 << 14};
     if constexpr (WARP_PER_CONTIG) {
         auto k1 = k1_count_warp<KA, KB, PALB, PERMUTE, WARPS>;
         const size_t smem = (size_t)(COLS + 32) * sizeof(uint32_t) * WARPS;
@@ -373,9 +376,10 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         const int64_t want = (n + WARPS - 1) / WARPS;
         if (grid > want) grid = want;
         if (grid < 1) grid = 1;
+        if (n < 2 * (int64_t)ctx->sm_count * per_sm * WARPS) lp = LongPolicy{4096, 4096};
         KbTimer t(ctx, 0);
         k1<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                              d_presence, ctx->d_k1_scratch, d_perm);
+                                                              d_presence, ctx->d_k1_scratch, d_perm, lp);
         ctx->launches++;
     } else {
         auto k1 = k1_count_cta<KA, KB, PALB, PERMUTE, THREADS>;
@@ -386,9 +390,10 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         int64_t grid = (int64_t)ctx->sm_count * per_sm;
         if (grid > n) grid = n;
         if (grid < 1) grid = 1;
+        if (n < 2 * (int64_t)ctx->sm_count * per_sm) lp = LongPolicy{16384, 8192};
         KbTimer t(ctx, 0);
         k1<<<(unsigned)grid, THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                               d_presence, ctx->d_k1_scratch, d_perm);
+                                                               d_presence, ctx->d_k1_scratch, d_perm, lp);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());
@@ -398,7 +403,7 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         KbTimer t(ctx, 1);
         k1l<<<(unsigned)(ctx->sm_count * 2), THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, d_counts, ld,
                                                                               d_exotic, d_presence,
-                                                                              ctx->d_k1_scratch, d_perm);
+                                                                              ctx->d_k1_scratch, d_perm, lp);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());

@@ -23,10 +23,19 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64
     else { p->bm = 64; p->bn = 64; }
     p->m_blocks = (nq + p->bm - 1) / p->bm;
     p->n_tiles = (nk + p->bn - 1) / p->bn;
-    int64_t want = (8LL * sm_count + p->m_blocks - 1) / p->m_blocks;   // >= ~8 units per SM
-    if (want > 16) want = 16;
-    if (want > p->n_tiles) want = p->n_tiles;
-    if (want < 1) want = 1;
+    // Splits: units = (query-block groups) x S are dealt round-robin to the resident CTAs (tensor path:
+    // CTA pairs, so sm_count/2 workers and groups of 2 blocks).  Pick S in [1,32] minimising the makespan
+    // rounds(S) * tiles_per_unit(S), charging half a tile per unit for list setup and write-back.
+    const int64_t cl = (impl == KB_KNN_TC && p->m_blocks >= 2) ? 2 : 1;
+    const int64_t groups = (p->m_blocks + cl - 1) / cl;
+    const int64_t workers = impl == KB_KNN_TC ? (sm_count / cl > 0 ? sm_count / cl : 1) : (int64_t)sm_count * 2;
+    int64_t want = 1; double best_cost = 1e300;
+    for (int64_t s_try = 1; s_try <= 32 && s_try <= p->n_tiles; ++s_try) {
+        const int64_t rounds = (groups * s_try + workers - 1) / workers;
+        const int64_t per_unit = (p->n_tiles + s_try - 1) / s_try;
+        const double cost = (double)rounds * ((double)per_unit + 0.5);
+        if (cost < best_cost * 0.995) { best_cost = cost; want = s_try; }
+    }
     if (const char* f = getenv("KB_KNN_SPLITS")) {              // experiments only
         const int64_t v = atoll(f);
         if (v >= 1) want = v < p->n_tiles ? v : p->n_tiles;

@@ -356,7 +356,11 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
     names = mode_column_names(mode)
     counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
     multi = group is not None and world > 1
-    if multi:
+    # every rank must agree on the column dictionary: MAX over the presence vectors.  On the optimistic
+    # path that only feeds the end-of-pass validation, so the vectors ride along with the k-list gather
+    # instead of paying for a collective of their own.
+    fold_presence = multi and optimistic and gather_lists and n_neighbors is not None
+    if multi and not fold_presence:
         import torch.distributed as dist
         dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)     # one D+1 word collective
     if optimistic:
@@ -434,13 +438,20 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
                                  flag_rows=flag_rows, flag_counts=flag_counts)
         if multi and gather_lists:
             # k-lists back to every rank: [idx | dist bits] packed per row, one collective
-            packed = torch.empty((per, 2 * n_neighbors), dtype=torch.int32, device=engine.device)
+            w2 = 2 * n_neighbors
+            extra = -(-(len(names) + 1) // w2) if fold_presence else 0      # rows that carry the presence words
+            packed = torch.empty((per + extra, w2), dtype=torch.int32, device=engine.device)
             if per > n:
-                packed[n:] = -1
+                packed[n:per] = -1
             packed[:n, :n_neighbors] = idx
             packed[:n, n_neighbors:] = dst.view(torch.int32)
-            g = all_gather_rows(packed, group)
-            out.update(all_idx=g[:, :n_neighbors], all_dist=g[:, n_neighbors:].view(torch.float32))
+            if extra:
+                packed[per:].view(-1)[:len(names) + 1] = presence
+            g = all_gather_rows(packed, group).view(world, per + extra, w2)
+            lists = g[:, :per].reshape(world * per, w2)
+            out.update(all_idx=lists[:, :n_neighbors], all_dist=lists[:, n_neighbors:].view(torch.float32))
+            if extra:
+                presence = g[:, per:].reshape(world, -1)[:, :len(names) + 1].max(dim=0).values.contiguous()
         out.update(idx=idx, dist=dst)
 
     # ---- validation (the only host synchronisation of an optimistic pass)
