@@ -373,6 +373,18 @@ def run_ours(a):
     ach_tf = flops / (gemm_ms / 1e3) / 1e12
     count_bytes = float(shard.offsets[-1]) + 4.0 * n * cols_full
     ach_gbs = count_bytes / (count_ms / 1e3) / 1e9
+    # the same counting kernel on north_star's dense 5120-column shape (supplementary: outside the timed region)
+    dense = None
+    if world == 1 and mode != _lib.KB_MODE_DENSE_5_6:
+        eng.stage_ms("count")
+        for _ in range(5):
+            eng.count(d_bases, d_offsets, n, _lib.KB_MODE_DENSE_5_6)
+        torch.cuda.synchronize()
+        dms, dn = eng.stage_ms("count")
+        dbytes = float(shard.offsets[-1]) + 4.0 * n * 5120
+        dense = {"bound": "hbm", "kernel": "k1_count (5120 dense columns)", "achieved": dbytes / (dms / 1e3) / 1e9,
+                 "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dbytes / (dms / 1e3) / 1e9 / pk["hbm_gbs"],
+                 "bytes_per_launch": dbytes, "launches": dn}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -391,6 +403,8 @@ def run_ours(a):
         "roofline_count": {"bound": "hbm", "kernel": "k1_count", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": ach_gbs / pk["hbm_gbs"], "bytes_per_launch": count_bytes},
     }
+    if dense:
+        line["roofline_count_dense5120"] = dense
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not a.no_cpu_baseline and asm is not None:
