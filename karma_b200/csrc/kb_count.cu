@@ -57,7 +57,13 @@ __device__ __forceinline__ uint32_t badbits4(uint32_t x) {
 // branch; a select + unconditional reduction is shorter and never diverges).
 __device__ __forceinline__ void red_shared_inc_if(uint32_t saddr, uint32_t dummy, uint32_t pred) {
     const uint32_t a = pred ? saddr : dummy;
+#if defined(KB_K1_EXPERIMENT) && KB_K1_EXPERIMENT == 1      // cost model only (WRONG counts): plain store instead of the reduction
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(pred) : "memory");
+#elif defined(KB_K1_EXPERIMENT) && KB_K1_EXPERIMENT == 2    // cost model only (WRONG counts): no shared-memory traffic at all
+    asm volatile("" ::"r"(a));
+#else
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+#endif
 }
 
 template <int KA, int KB, bool PALB>
@@ -67,23 +73,42 @@ struct Bins {
     static constexpr int TOTAL = A + B;
 };
 
+// kmer.py:172-177 column order of "5p6" (sorted(): a palindromic 6-mer follows its 5-mer prefix):
+//   column(5-mer code c) = c + #{palindromic 6-mers sorting before it}
+//   column(palindromic 6-mer of rank r = 16*x1+4*x2+x3) = 272*x1 + 69*x2 + 21*x3 + 1
+// (closed forms checked against sorted() in tests/test_oracle_golden.py::test_full_column_set_ka6).
+__device__ __forceinline__ uint32_t sorted_col_5mer(uint32_t c) {
+    const uint32_t d1 = c >> 8, d2 = (c >> 6) & 3u;
+    const int cc = (int)(c & 63u) - (int)d2;
+    const uint32_t t = cc <= 0 ? 0u : (uint32_t)min(4, (cc + 19) / 20);
+    return c + 16u * d1 + 4u * d2 + t;
+}
+__device__ __forceinline__ uint32_t sorted_col_pal6(uint32_t r) {
+    return 272u * (r >> 4) + 69u * ((r >> 2) & 3u) + 21u * (r & 3u) + 1u;
+}
+
 // Warp-cooperative accumulation of the windows starting in [lo, hi) of the contig at
 // absolute byte `beg` (length L) into `hist`.  The warp walks 512-byte spans starting
 // at the 16-byte aligned absolute address A_first, stepping A_stride; lane l owns the
-// 16 window starts of bytes [A0+16l, A0+16l+16) and needs 8 halo bytes, which are the
-// next lane's first bases (one shuffle; lane 31 loads its own).  Returns the lane's
-// tally of windows that contain a non-ACGT byte.
-template <int KA, int KB, bool PALB>
+// 16 window starts of bytes [A0+16l, A0+16l+16) and loads 8 halo bytes (an L1 hit: they
+// are the next lane's first bases).  SORTED: the histogram is kept in kmer.py's sorted
+// column order through a byte-offset table (`lut`, 1024 x u16 in shared memory), so the
+// row flush is a straight copy.  Returns the lane's tally of windows with a non-ACGT byte.
+template <int KA, int KB, bool PALB, bool SORTED>
 __device__ __forceinline__ uint32_t accumulate_warp(const uint8_t* __restrict__ bases, int64_t beg, int64_t L,
                                                     int64_t lo, int64_t hi, uint32_t* hist, uint32_t* dummy,
+                                                    const uint16_t* lut,
                                                     int64_t A_first, int64_t A_stride, int lane) {
     constexpr int KMAX = (KB > KA) ? KB : KA;
     static_assert(KMAX <= 8, "8 halo bases cover k <= 8 only");
+    static_assert(!SORTED || (KA == 5 && KB == 6 && PALB), "sorted layout is the 5p6 mode");
     constexpr uint32_t BINS_A = Bins<KA, KB, PALB>::A;
     uint32_t exotic = 0;
     const int64_t end_abs = beg + L;
     const uint32_t h32 = (uint32_t)__cvta_generic_to_shared(hist);
     const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dummy);
+    const int64_t hiA64 = (hi < L - KA + 1) ? hi : (L - KA + 1);
+    const int64_t hiB64 = (KB > 0) ? ((hi < L - KB + 1) ? hi : (L - KB + 1)) : 0;
     for (int64_t A0 = A_first; A0 < beg + hi; A0 += A_stride) {          // warp-uniform trip count
         const int64_t A = A0 + 16 * lane;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -104,12 +129,14 @@ __device__ __forceinline__ uint32_t accumulate_warp(const uint8_t* __restrict__ 
             bad = (badbits4(x0) << 20) | (badbits4(x1) << 16) | (badbits4(x2) << 12) | (badbits4(x3) << 8) |
                   (badbits4(y0) << 4) | badbits4(y1);
         }
-        const int64_t s0 = A - beg;                                      // contig position of base 0 (may be < 0)
-        const int64_t wlo64 = lo - s0;
-        const int wlo = wlo64 > 0 ? (wlo64 < 16 ? (int)wlo64 : 16) : 0;
+        // window range of this lane in 32-bit arithmetic: span-uniform 64-bit differences, clamped, then per lane
+        const int64_t S0 = A0 - beg;                                     // contig position of lane 0's base 0 (may be < 0)
+        const int64_t c_lo = lo - S0, c_hiA = hiA64 - S0;
+        const int dlo = (int)(c_lo < -1 ? -1 : (c_lo > 1024 ? 1024 : c_lo)) - 16 * lane;
+        const int dhiA = (int)(c_hiA < -1 ? -1 : (c_hiA > 1024 ? 1024 : c_hiA)) - 16 * lane;
+        const int wlo = min(max(dlo, 0), 16);
         // ---- component A: window w <-> bit 23-w
-        const int64_t whiA64 = ((hi < L - KA + 1) ? hi : (L - KA + 1)) - s0;
-        const int whiA = whiA64 < 0 ? 0 : (whiA64 < 16 ? (int)whiA64 : 16);
+        const int whiA = min(max(dhiA, 0), 16);
         const uint32_t rA = whiA > wlo ? (1u << (24 - wlo)) - (1u << (24 - whiA)) : 0u;
         uint32_t BA = bad;
 #pragma unroll
@@ -117,11 +144,15 @@ __device__ __forceinline__ uint32_t accumulate_warp(const uint8_t* __restrict__ 
         const uint32_t okA = rA & ~BA;
         exotic += __popc(rA & BA);
 #pragma unroll
-        for (int w = 0; w < 16; ++w)
-            red_shared_inc_if(h32 + 4u * ((uint32_t)(codes >> (2 * (24 - KA - w))) & (BINS_A - 1)), d32, okA & (1u << (23 - w)));
+        for (int w = 0; w < 16; ++w) {
+            const uint32_t code = (uint32_t)(codes >> (2 * (24 - KA - w))) & (BINS_A - 1);
+            const uint32_t off = SORTED ? (uint32_t)lut[code] : 4u * code;
+            red_shared_inc_if(h32 + off, d32, okA & (1u << (23 - w)));
+        }
         if constexpr (KB > 0) {
-            const int64_t whiB64 = ((hi < L - KB + 1) ? hi : (L - KB + 1)) - s0;
-            const int whiB = whiB64 < 0 ? 0 : (whiB64 < 16 ? (int)whiB64 : 16);
+            const int64_t c_hiB = hiB64 - S0;
+            const int dhiB = (int)(c_hiB < -1 ? -1 : (c_hiB > 1024 ? 1024 : c_hiB)) - 16 * lane;
+            const int whiB = min(max(dhiB, 0), 16);
             const uint32_t rB = whiB > wlo ? (1u << (24 - wlo)) - (1u << (24 - whiB)) : 0u;
             uint32_t BB = bad;
 #pragma unroll
@@ -142,7 +173,9 @@ __device__ __forceinline__ uint32_t accumulate_warp(const uint8_t* __restrict__ 
                 uint64_t pm = ~np & ((uint64_t)sp << 16);               // valid palindromic windows (~1/64 of all)
                 while (__any_sync(FULL, pm != 0)) {                     // warp-uniform trip count: no divergence
                     const int b = pm ? 63 - __clzll((long long)pm) : 4;
-                    red_shared_inc_if(h32 + 4u * (BINS_A + ((uint32_t)(codes >> (b - 4)) & 63u)), d32, pm != 0);
+                    const uint32_t r = (uint32_t)(codes >> (b - 4)) & 63u;
+                    const uint32_t col = SORTED ? sorted_col_pal6(r) : BINS_A + r;
+                    red_shared_inc_if(h32 + 4u * col, d32, pm != 0);
                     pm &= ~(1ull << b);
                 }
             } else {
@@ -163,9 +196,8 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 
 // Flush one histogram (group of NT threads, this thread = tid) to a count row with 128-bit
 // stores, clear it, and collect presence bits (bit 4*it+j for vector tid+it*NT, element j).
-template <int COLS, bool PERMUTE, int NT>
-__device__ __forceinline__ void flush_row(uint32_t* hist, uint32_t* __restrict__ row_out,
-                                          const uint16_t* __restrict__ perm, int tid, uint64_t& pres) {
+template <int COLS, int NT>
+__device__ __forceinline__ void flush_row(uint32_t* hist, uint32_t* __restrict__ row_out, int tid, uint64_t& pres) {
     constexpr int VEC = COLS / 4;
     constexpr int ITERS = (VEC + NT - 1) / NT;
     static_assert(COLS % 4 == 0, "row flush is 128-bit");
@@ -175,15 +207,8 @@ __device__ __forceinline__ void flush_row(uint32_t* hist, uint32_t* __restrict__
     for (int it = 0; it < ITERS; ++it) {
         const int i = tid + it * NT;
         if (i < VEC) {
-            uint4 r;
-            if constexpr (PERMUTE) {
-                const ushort4 p = *reinterpret_cast<const ushort4*>(perm + 4 * i);
-                r = make_uint4(hist[p.x], hist[p.y], hist[p.z], hist[p.w]);
-                hist[p.x] = 0; hist[p.y] = 0; hist[p.z] = 0; hist[p.w] = 0;
-            } else {
-                r = *reinterpret_cast<uint4*>(hist + 4 * i);
-                *reinterpret_cast<uint4*>(hist + 4 * i) = make_uint4(0, 0, 0, 0);
-            }
+            const uint4 r = *reinterpret_cast<uint4*>(hist + 4 * i);
+            *reinterpret_cast<uint4*>(hist + 4 * i) = make_uint4(0, 0, 0, 0);
             __stcs(out + i, r);                                          // streaming: the row is not re-read here
             pres |= (uint64_t)((r.x != 0) | ((r.y != 0) << 1) | ((r.z != 0) << 2) | ((r.w != 0) << 3)) << (4 * it);
         }
@@ -210,17 +235,21 @@ __device__ __forceinline__ void publish_presence(uint32_t* __restrict__ presence
 // scratch[4..] = rows of the long contigs
 
 // ---- one WARP per contig (histogram <= 8 KB): no block barriers, 8 independent warps per CTA
-template <int KA, int KB, bool PALB, bool PERMUTE, int WARPS>
+template <int KA, int KB, bool PALB, bool SORTED, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
               uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm, LongPolicy lp) {
+              uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     extern __shared__ __align__(16) uint32_t smem_hist[];
     const int lane = threadIdx.x & 31;
-    uint32_t* hist = smem_hist + (threadIdx.x >> 5) * (COLS + 32);   // + one dummy word per lane
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem_hist);            // SORTED: 1024 x u16 byte offsets (2 KB)
+    uint32_t* hist = smem_hist + (SORTED ? 512 : 0) + (threadIdx.x >> 5) * (COLS + 32);   // + one dummy word per lane
+    if constexpr (SORTED) {
+        for (int c = threadIdx.x; c < 1024; c += WARPS * 32) lut[c] = (uint16_t)(4u * sorted_col_5mer((uint32_t)c));
+    }
     for (int i = lane; i < COLS; i += 32) hist[i] = 0;
-    __syncwarp();
+    __syncthreads();
     uint64_t pres = 0;
     while (true) {
         int64_t row = 0;
@@ -240,7 +269,7 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
             for (int i = lane; i < COLS / 4; i += 32) reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
             continue;
         }
-        const uint32_t ex = accumulate_warp<KA, KB, PALB>(bases, beg, L, 0, L, hist, hist + COLS + lane, beg & ~int64_t(15), 512, lane);
+        const uint32_t ex = accumulate_warp<KA, KB, PALB, SORTED>(bases, beg, L, 0, L, hist, hist + COLS + lane, lut, beg & ~int64_t(15), 512, lane);
         const uint32_t ex_total = warp_sum(ex);
         if (lane == 0) {
             if (exotic_out) exotic_out[row] = ex_total;
@@ -250,23 +279,28 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
             }
         }
         __syncwarp();
-        flush_row<COLS, PERMUTE, 32>(hist, out, perm, lane, pres);
+        flush_row<COLS, 32>(hist, out, lane, pres);
         __syncwarp();
     }
     publish_presence<COLS, 32>(presence, lane, pres);
 }
 
 // ---- one CTA per contig (histograms of 16-64 KB)
-template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
+template <int KA, int KB, bool PALB, bool SORTED, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
              uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-             uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm, LongPolicy lp) {
+             uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
-    extern __shared__ __align__(16) uint32_t hist[];
+    extern __shared__ __align__(16) uint32_t smem_hist[];
     __shared__ uint32_t s_red[THREADS / 32];
     __shared__ int64_t s_row;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem_hist);
+    uint32_t* hist = smem_hist + (SORTED ? 512 : 0);
+    if constexpr (SORTED) {
+        for (int c = threadIdx.x; c < 1024; c += THREADS) lut[c] = (uint16_t)(4u * sorted_col_5mer((uint32_t)c));
+    }
     for (int i = threadIdx.x; i < COLS; i += THREADS) hist[i] = 0;
     uint64_t pres = 0;
     while (true) {
@@ -287,8 +321,8 @@ k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offs
             for (int i = threadIdx.x; i < COLS / 4; i += THREADS) reinterpret_cast<uint4*>(out)[i] = make_uint4(0, 0, 0, 0);
             continue;
         }
-        const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB>(bases, beg, L, 0, L, hist, hist + COLS + threadIdx.x,
-                                                                  (beg & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
+        const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB, SORTED>(bases, beg, L, 0, L, hist, hist + COLS + threadIdx.x, lut,
+                                                                          (beg & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
         if (lane == 0) s_red[warp] = ex;
         __syncthreads();                                         // all atomics done, s_red visible
         if (threadIdx.x == 0) {
@@ -300,22 +334,27 @@ k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offs
                 if (presence) presence[COLS] = 1u;
             }
         }
-        flush_row<COLS, PERMUTE, THREADS>(hist, out, perm, threadIdx.x, pres);
+        flush_row<COLS, THREADS>(hist, out, threadIdx.x, pres);
     }
     publish_presence<COLS, THREADS>(presence, threadIdx.x, pres);
 }
 
 // ---- split path: every CTA walks the long-contig list and takes chunks blockIdx.x, +gridDim.x, ...
-template <int KA, int KB, bool PALB, bool PERMUTE, int THREADS>
+template <int KA, int KB, bool PALB, bool SORTED, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets,
               uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-              uint32_t* __restrict__ presence, int32_t* scratch, const uint16_t* __restrict__ perm, LongPolicy lp) {
+              uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
-    extern __shared__ __align__(16) uint32_t hist[];
+    extern __shared__ __align__(16) uint32_t smem_hist[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_long = scratch[1];
     if (n_long == 0) return;
+    uint16_t* lut = reinterpret_cast<uint16_t*>(smem_hist);
+    uint32_t* hist = smem_hist + (SORTED ? 512 : 0);
+    if constexpr (SORTED) {
+        for (int c = threadIdx.x; c < 1024; c += THREADS) lut[c] = (uint16_t)(4u * sorted_col_5mer((uint32_t)c));
+    }
     for (int i = threadIdx.x; i < COLS; i += THREADS) hist[i] = 0;
     __syncthreads();
     for (int li = 0; li < n_long; ++li) {
@@ -326,8 +365,8 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
         for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
             const int64_t lo = c * lp.chunk;
             const int64_t hi = (lo + lp.chunk < L) ? lo + lp.chunk : L;
-            const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB>(bases, beg, L, lo, hi, hist, hist + COLS + threadIdx.x,
-                                                                      ((beg + lo) & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
+            const uint32_t ex = warp_sum(accumulate_warp<KA, KB, PALB, SORTED>(bases, beg, L, lo, hi, hist, hist + COLS + threadIdx.x, lut,
+                                                                              ((beg + lo) & ~int64_t(15)) + 512 * warp, 16 * THREADS, lane));
             if (lane == 0 && ex) {
                 if (exotic_out) atomicAdd(&exotic_out[row], ex);
                 atomicAdd(reinterpret_cast<unsigned long long*>(scratch + 2), (unsigned long long)ex);
@@ -336,11 +375,10 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
             __syncthreads();
             uint32_t* out = counts + row * ld;
             for (int i = threadIdx.x; i < COLS; i += THREADS) {
-                const int src = PERMUTE ? (int)perm[i] : i;
-                const uint32_t v = hist[src];
+                const uint32_t v = hist[i];
                 if (v) {
                     atomicAdd(&out[i], v);
-                    hist[src] = 0;
+                    hist[i] = 0;
                     if (presence) presence[i] = 1u;
                 }
             }
@@ -349,10 +387,9 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
     }
 }
 
-template <int KA, int KB, bool PALB, bool PERMUTE>
+template <int KA, int KB, bool PALB, bool SORTED>
 int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_t n,
-           uint32_t* d_counts, int64_t ld, uint32_t* d_exotic, uint32_t* d_presence,
-           const uint16_t* d_perm) {
+           uint32_t* d_counts, int64_t ld, uint32_t* d_exotic, uint32_t* d_presence) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     constexpr bool WARP_PER_CONTIG = COLS <= 2048;
     constexpr int WARPS = 8;
@@ -366,11 +403,11 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         ctx->k1_scratch_cap = need;
     }
     KB_CUDA(cudaMemsetAsync(ctx->d_k1_scratch, 0, 4 * sizeof(int32_t), ctx->stream));
-    const size_t smem_one = (size_t)(COLS + THREADS) * sizeof(uint32_t);   // histogram + dummy words
+    const size_t smem_one = (size_t)(COLS + THREADS) * sizeof(uint32_t) + (SORTED ? 2048 : 0);   // histogram + dummy words (+ column table)
     LongPolicy lp{1 << 16, 1 << 14};
     if constexpr (WARP_PER_CONTIG) {
-        auto k1 = k1_count_warp<KA, KB, PALB, PERMUTE, WARPS>;
-        const size_t smem = (size_t)(COLS + 32) * sizeof(uint32_t) * WARPS;
+        auto k1 = k1_count_warp<KA, KB, PALB, SORTED, WARPS>;
+        const size_t smem = (size_t)(COLS + 32) * sizeof(uint32_t) * WARPS + (SORTED ? 2048 : 0);
         KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, WARPS * 32, smem));
@@ -382,10 +419,10 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         if (n < 2 * (int64_t)ctx->sm_count * per_sm * WARPS) lp = LongPolicy{4096, 4096};
         KbTimer t(ctx, 0);
         k1<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                              d_presence, ctx->d_k1_scratch, d_perm, lp);
+                                                              d_presence, ctx->d_k1_scratch, lp);
         ctx->launches++;
     } else {
-        auto k1 = k1_count_cta<KA, KB, PALB, PERMUTE, THREADS>;
+        auto k1 = k1_count_cta<KA, KB, PALB, SORTED, THREADS>;
         KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
         int per_sm = 0;
         KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, THREADS, smem_one));
@@ -396,44 +433,20 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         if (n < 2 * (int64_t)ctx->sm_count * per_sm) lp = LongPolicy{16384, 8192};
         KbTimer t(ctx, 0);
         k1<<<(unsigned)grid, THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                               d_presence, ctx->d_k1_scratch, d_perm, lp);
+                                                               d_presence, ctx->d_k1_scratch, lp);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());
     {
-        auto k1l = k1_count_long<KA, KB, PALB, PERMUTE, THREADS>;
+        auto k1l = k1_count_long<KA, KB, PALB, SORTED, THREADS>;
         KB_CUDA(cudaFuncSetAttribute(k1l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
         KbTimer t(ctx, 1);
         k1l<<<(unsigned)(ctx->sm_count * 2), THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, d_counts, ld,
                                                                               d_exotic, d_presence,
-                                                                              ctx->d_k1_scratch, d_perm, lp);
+                                                                              ctx->d_k1_scratch, lp);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());
-    return KB_OK;
-}
-
-uint16_t* g_perm_5p6[16] = {nullptr};   // per device
-
-// kmer.py:172-177: sorted() over {5-mers} U {string-palindromic 6-mers}.  For ACGT,
-// palindromic 6-mer x1x2x3x3x2x1 sorts directly after its 5-mer prefix x1x2x3x3x2.
-int build_perm_5p6(int device, const uint16_t** out) {
-    if (device < 0 || device >= 16) { kb_set_error("device index out of range"); return KB_EINVAL; }
-    if (!g_perm_5p6[device]) {
-        uint16_t h[1088];
-        int o = 0;
-        for (int c = 0; c < 1024; ++c) {
-            h[o++] = (uint16_t)c;
-            const int x1 = c >> 8, x2 = (c >> 6) & 3, x3 = (c >> 4) & 3, x4 = (c >> 2) & 3, x5 = c & 3;
-            if (x4 == x3 && x5 == x2) h[o++] = (uint16_t)(1024 + (x1 << 4 | x2 << 2 | x3));
-        }
-        if (o != 1088) { kb_set_error("internal: 5p6 permutation has %d entries", o); return KB_EINVAL; }
-        uint16_t* d = nullptr;
-        KB_CUDA(cudaMalloc(&d, sizeof(h)));
-        KB_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
-        g_perm_5p6[device] = d;
-    }
-    *out = g_perm_5p6[device];
     return KB_OK;
 }
 
@@ -443,23 +456,18 @@ int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases
                             const int64_t* d_offsets, int64_t n, uint32_t* d_counts,
                             int64_t ld, uint32_t* d_exotic, uint32_t* d_presence) {
 #define KB_ARGS ctx, d_bases, d_offsets, n, d_counts, ld, d_exotic, d_presence
-    if (m.permute) {
-        const uint16_t* perm = nullptr;
-        int rc = build_perm_5p6(ctx->device, &perm);
-        if (rc) return rc;
-        return launch<5, 6, true, true>(KB_ARGS, perm);
-    }
-    if (m.ka == 5 && m.kb == 6) return launch<5, 6, false, false>(KB_ARGS, nullptr);
-    if (m.ka == 4 && m.kb == 5) return launch<4, 5, false, false>(KB_ARGS, nullptr);
+    if (m.permute) return launch<5, 6, true, true>(KB_ARGS);     // kmer.py's sorted() column order
+    if (m.ka == 5 && m.kb == 6) return launch<5, 6, false, false>(KB_ARGS);
+    if (m.ka == 4 && m.kb == 5) return launch<4, 5, false, false>(KB_ARGS);
     if (m.kb == 0) {
         switch (m.ka) {
-            case 1: return launch<1, 0, false, false>(KB_ARGS, nullptr);
-            case 2: return launch<2, 0, false, false>(KB_ARGS, nullptr);
-            case 3: return launch<3, 0, false, false>(KB_ARGS, nullptr);
-            case 4: return launch<4, 0, false, false>(KB_ARGS, nullptr);
-            case 5: return launch<5, 0, false, false>(KB_ARGS, nullptr);
-            case 6: return launch<6, 0, false, false>(KB_ARGS, nullptr);
-            case 7: return launch<7, 0, false, false>(KB_ARGS, nullptr);
+            case 1: return launch<1, 0, false, false>(KB_ARGS);
+            case 2: return launch<2, 0, false, false>(KB_ARGS);
+            case 3: return launch<3, 0, false, false>(KB_ARGS);
+            case 4: return launch<4, 0, false, false>(KB_ARGS);
+            case 5: return launch<5, 0, false, false>(KB_ARGS);
+            case 6: return launch<6, 0, false, false>(KB_ARGS);
+            case 7: return launch<7, 0, false, false>(KB_ARGS);
         }
     }
 #undef KB_ARGS
