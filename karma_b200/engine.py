@@ -205,8 +205,41 @@ class Engine:
         d_key_len = hk.to(self.device, non_blocking=True)
         return d_bases, d_offsets, d_key_len
 
+    def upload_chunked(self, bases, offsets, key_len, n_chunks):
+        """Like upload(), but the bases go up in ``n_chunks`` row chunks on a copy stream, each
+        followed by an event, so that counting (and the profile download, which uses the other
+        DMA direction) can start while the rest of the assembly is still in flight.
+        Returns (d_bases, d_offsets, d_key_len, [(row_lo, row_hi, event), ...])."""
+        n = len(offsets) - 1
+        total = int(offsets[-1])
+        cap = (total + 15) // 16 * 16 + 32
+        d_bases = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        hb = bases if isinstance(bases, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bases))
+        ho = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
+        hk = key_len if isinstance(key_len, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(key_len, dtype=np.int32))
+        main = torch.cuda.current_stream(self.device)
+        up = self.__dict__.setdefault("_up", None) or torch.cuda.Stream(self.device)
+        self._up = up
+        up.wait_stream(main)
+        chunks = []
+        with torch.cuda.stream(up):
+            d_offsets = ho.to(self.device, non_blocking=True)
+            d_key_len = hk.to(self.device, non_blocking=True)
+            for c in range(n_chunks):
+                lo, hi = n * c // n_chunks, n * (c + 1) // n_chunks
+                b0, b1 = int(ho[lo]), int(ho[hi])
+                if b1 > b0:
+                    d_bases[b0:b1].copy_(hb[b0:b1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+                chunks.append((lo, hi, ev))
+        d_bases.record_stream(up)                      # allocated for the main stream, filled on the copy stream
+        d_offsets.record_stream(main)                  # allocated on the copy stream, consumed on the main stream
+        d_key_len.record_stream(main)
+        return d_bases, d_offsets, d_key_len, chunks
+
     # ---- K1 ----------------------------------------------------------------------
-    def count(self, d_bases, d_offsets, n, mode, counts=None, exotic=None, presence=None):
+    def count(self, d_bases, d_offsets, n, mode, counts=None, exotic=None, presence=None, zero_presence=True):
         """u32 counts (n, D) [torch.int32 storage], exotic tallies (n,), presence (D+1,):
         presence[c] != 0 iff column c occurs, presence[D] != 0 iff a window holds a non-ACGT byte."""
         self._bind_stream()
@@ -217,7 +250,8 @@ class Engine:
             exotic = torch.empty(n, dtype=torch.int32, device=self.device)
         if presence is None:
             presence = torch.empty(cols + 1, dtype=torch.int32, device=self.device)
-        presence.zero_()
+        if zero_presence:
+            presence.zero_()
         check(self.lib.kb_count(self.ctx, mode, ptr(d_bases), ptr(d_offsets), n, ptr(counts), counts.stride(0),
                                 ptr(exotic), ptr(presence)))
         return counts, exotic, presence
@@ -277,7 +311,7 @@ class Engine:
 
     # ---- K3 ------------------------------------------------------------------------
     def normalise(self, counts, d_cols, d_key_len, want_profile=True, want_operand=True, profile=None,
-                  rows_alloc=None):
+                  rows_alloc=None, launch=True):
         """K3.  With ``rows_alloc`` > n the kNN inputs are allocated with that many rows
         (the equal-size shard a rank contributes to the all-gather); the padding rows are
         zero counts, key_len 1 and flagged so that they can never be neighbours."""
@@ -295,10 +329,21 @@ class Engine:
             if operand is not None:
                 operand[n:] = 0
             rowmeta[n:] = torch.tensor([0, 0, 1, 11], dtype=torch.int32, device=self.device)   # flags 1|2|8: padding
-        check(self.lib.kb_normalise(self.ctx, ptr(counts), counts.stride(0), d_cols, ptr(d_key_len), n,
-                                    ptr(profile) if want_profile else None, ldp,
-                                    ptr(operand), dp, ptr(rowmeta)))
+        if launch:
+            self.normalise_rows(counts, d_cols, d_key_len, 0, n, profile, operand, rowmeta)
         return profile, operand, rowmeta
+
+    def normalise_rows(self, counts, d_cols, d_key_len, lo, hi, profile, operand, rowmeta):
+        """K3 on rows [lo, hi) of preallocated outputs (the chunked upload path runs it per chunk)."""
+        self._bind_stream()
+        if hi <= lo:
+            return
+        c = counts[lo:hi]
+        check(self.lib.kb_normalise(self.ctx, ptr(c), counts.stride(0), d_cols, ptr(d_key_len[lo:hi]), hi - lo,
+                                    ptr(profile[lo:hi]) if profile is not None else None,
+                                    profile.stride(0) if profile is not None else 0,
+                                    ptr(operand[lo:hi]) if operand is not None else None,
+                                    operand.stride(0) if operand is not None else 0, ptr(rowmeta[lo:hi])))
 
     # ---- K4 + K5 ---------------------------------------------------------------------
     def knn(self, operand, rowmeta, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False,
@@ -338,7 +383,7 @@ def all_gather_rows(t, group):
 
 def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
                 want_profile=True, group=None, rank=0, world=1, n_total=None, gather_lists=False, bufs=None,
-                on_profile=None, optimistic=True, row0=0):
+                on_profile=None, optimistic=True, row0=0, chunks=None):
     """The hot path on device-resident inputs: K1 -> column dictionary (-> K1x/K2) -> K3
     [-> all-gather of the operand shards -> K4 (-> K4x) -> K5].  Returns device tensors plus
     the column list.
@@ -349,13 +394,37 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
     back asynchronously and VALIDATED at the end (one synchronisation per pass).  If the
     assumption fails the pass is redone on the general path (compaction, exotic keys, exact
     side path).  ``bufs``: optional preallocated counts/exotic/presence tensors.
-    ``on_profile(profile)`` is called as soon as K3 has been enqueued (to start its D2H)."""
+    ``on_profile(profile, lo, hi)`` is called as soon as K3 of rows [lo, hi) has been enqueued
+    (to start their D2H).  ``chunks`` = [(row_lo, row_hi, event)] from upload_chunked: the
+    optimistic pass then counts/normalises chunk by chunk as the uploads land."""
     mode = mode_of(kmer_size)
     b = bufs or {}
     faithful = mode == KB_MODE_5P6 or mode >= 16
     names = mode_column_names(mode)
-    counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
+    main = torch.cuda.current_stream(engine.device)
     multi = group is not None and world > 1
+    if chunks and not optimistic:
+        for _, _, ev in chunks:
+            main.wait_event(ev)
+        chunks = None
+    if chunks:
+        cols_full = len(names)
+        counts = b.get("counts") if b.get("counts") is not None else torch.empty((n, cols_full), dtype=torch.int32, device=engine.device)
+        exotic = b.get("exotic") if b.get("exotic") is not None else torch.empty(n, dtype=torch.int32, device=engine.device)
+        presence = b.get("presence") if b.get("presence") is not None else torch.empty(cols_full + 1, dtype=torch.int32, device=engine.device)
+        presence.zero_()
+        per = shard_bounds(n_total, world, rank)[2] if multi else None
+        profile, operand, rowmeta = engine.normalise(counts, cols_full, d_key_len, want_profile=want_profile,
+                                                     want_operand=n_neighbors is not None, rows_alloc=per, launch=False)
+        for lo, hi, ev in chunks:
+            main.wait_event(ev)
+            if hi > lo:
+                engine.count(d_bases, d_offsets[lo:], hi - lo, mode, counts[lo:hi], exotic[lo:hi], presence, zero_presence=False)
+                engine.normalise_rows(counts, cols_full, d_key_len, lo, hi, profile, operand, rowmeta)
+                if on_profile is not None and profile is not None:
+                    on_profile(profile, lo, hi)
+    else:
+        counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
     # every rank must agree on the column dictionary: MAX over the presence vectors.  On the optimistic
     # path that only feeds the end-of-pass validation, so the vectors ride along with the k-list gather
     # instead of paying for a collective of their own.
@@ -378,10 +447,11 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
     if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
         counts = counts.contiguous()
     per = shard_bounds(n_total, world, rank)[2] if multi else None
-    profile, operand, rowmeta = engine.normalise(
-        counts, d_cols, d_key_len, want_profile=want_profile, want_operand=n_neighbors is not None, rows_alloc=per)
-    if on_profile is not None and profile is not None:
-        on_profile(profile)
+    if not chunks:
+        profile, operand, rowmeta = engine.normalise(
+            counts, d_cols, d_key_len, want_profile=want_profile, want_operand=n_neighbors is not None, rows_alloc=per)
+        if on_profile is not None and profile is not None:
+            on_profile(profile, 0, n)
     out = {"columns": columns, "d_cols": d_cols, "counts": counts, "profile": profile, "operand": operand,
            "rowmeta": rowmeta, "idx": None, "dist": None}
     all_op, all_meta = operand, rowmeta
@@ -470,7 +540,8 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
             redo = True
         if redo:
             return device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors, impl, want_profile,
-                               group, rank, world, n_total, gather_lists, bufs, on_profile, optimistic=False, row0=row0)
+                               group, rank, world, n_total, gather_lists, bufs, on_profile, optimistic=False, row0=row0,
+                               chunks=None)
     if flags_or & 4:
         # a contig shorter than k (kmer.py:250-258): report the first such row of this rank
         own = rowmeta[:n, 3].cpu().numpy()
@@ -498,25 +569,33 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
     by the next call (a serving loop); otherwise every call returns fresh arrays.
     """
     n = len(offsets) - 1
-    d_bases, d_offsets, d_key_len = engine.upload(bases, offsets, key_len)
     main = torch.cuda.current_stream(engine.device)
     side = engine.side_stream()
+    chunks = None
+    if n >= 4096:
+        # H2D in row chunks: counting and the (opposite-direction) profile download start early
+        d_bases, d_offsets, d_key_len, chunks = engine.upload_chunked(bases, offsets, key_len, 4)
+    else:
+        d_bases, d_offsets, d_key_len = engine.upload(bases, offsets, key_len)
     hold = {}
 
-    def start_download(profile):
-        # D2H of the profile on the side stream, ordered after K3, overlapping the kNN
-        h = engine.host_buffer("profile", tuple(profile.shape), torch.float64, reuse_host)
+    def start_download(profile, lo, hi):
+        # D2H of profile rows [lo, hi) on the side stream, ordered after their K3, overlapping
+        # the remaining uploads and the kNN
+        h = hold.get("profile")
+        if h is None or tuple(h.shape) != tuple(profile.shape):
+            h = engine.host_buffer("profile", tuple(profile.shape), torch.float64, reuse_host)
+            hold["profile"] = h
         ready = torch.cuda.Event()
         ready.record(main)
         side.wait_event(ready)
         with torch.cuda.stream(side):
-            h.copy_(profile, non_blocking=True)
+            h[lo:hi].copy_(profile[lo:hi], non_blocking=True)
         profile.record_stream(side)
-        hold["profile"] = h
 
     r = device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors=n_neighbors, impl=impl,
                     want_profile=want_profile, group=group, rank=rank, world=world, n_total=n_total,
-                    on_profile=start_download if want_profile else None, row0=row0)
+                    on_profile=start_download if want_profile else None, row0=row0, chunks=chunks)
     out = {"columns": r["columns"], "profile": None, "knn_idx": None, "knn_dist": None,
            "d_profile": r["profile"], "d_operand": r["operand"]}
     if n_neighbors is not None:
