@@ -211,11 +211,35 @@ KB_API int kb_fasta_fill(kb_fasta* f, uint8_t* h_bases, int64_t* h_offsets, int3
                   uint8_t* h_keys, int64_t* h_key_offsets);
 KB_API int kb_fasta_close(kb_fasta* f);
 
+/* ---- read graph from salmon equivalence classes (separate path) -----
+ * Replaces the loops of ReadGraph.from_equivalence_classes (read_graph.py:61-148).
+ * kb_eq_open parses eq_classes.txt (read_graph.py:75-82: contig count, ignored line, names,
+ * then "first<TAB>id...<TAB>count" lines) into CSR arrays; kb_eq_fill copies them out:
+ *  h_names uint8[name_bytes], h_name_off int64[n+1], h_class_off int64[C+1], h_ids int32[n_ids],
+ *  h_counts int64[C], h_skip uint8[C] (1 iff the first token is "1": read_graph.py:102 skips
+ *  those classes when pairing).
+ * kb_readgraph_build (device inputs, synchronises): d_totals uint64[n_contigs] receives the
+ * reads per contig (read_graph.py:86-93); the unique contig pairs with their shared read
+ * counts and weights ((shared/totA)+(shared/totB))/2 are kept in the context in exactly the
+ * order networkx's graph.edges() yields them in the reference; kb_readgraph_fetch copies
+ * them to the host (edges with shared == 0 are included; the reference drops them). */
+typedef struct kb_eq kb_eq;
+KB_API int kb_eq_open(const char* path, kb_eq** out, int64_t* n_contigs, int64_t* n_classes, int64_t* n_ids,
+               int64_t* name_bytes);
+KB_API int kb_eq_fill(kb_eq* q, uint8_t* h_names, int64_t* h_name_off, int64_t* h_class_off, int32_t* h_ids,
+               int64_t* h_counts, uint8_t* h_skip);
+KB_API int kb_eq_close(kb_eq* q);
+KB_API int kb_readgraph_build(kb_ctx* ctx, int64_t n_contigs, int64_t n_classes, const int64_t* d_class_off,
+                       const int32_t* d_ids, const int64_t* d_counts, const uint8_t* d_skip,
+                       uint64_t* d_totals, int64_t* n_edges);
+KB_API int kb_readgraph_fetch(kb_ctx* ctx, int32_t* h_a, int32_t* h_b, double* h_weight, uint64_t* h_shared);
+
 /* Per-stage device times.  With timing enabled every launch of a stage is bracketed
  * by a CUDA-event pair on the context stream (a ring of 128 pairs per stage).
  * kb_stage_ms synchronises, returns the mean duration (ms) and the number of launches
  * recorded since the last read, and resets the stage.
- *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank, 6 exact side path */
+ *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank, 6 exact side path,
+ *         7 read-graph build */
 KB_API int kb_enable_timing(kb_ctx* ctx, int on);
 KB_API int kb_stage_ms(kb_ctx* ctx, int which, float* mean_ms, int* n_launches);
 /* Number of kernels this library launched since the context was created. */

@@ -17,7 +17,7 @@ KB_MODE_DENSE_4_5 = 2
 KB_KNN_AUTO, KB_KNN_SIMT, KB_KNN_TC = 0, 1, 2
 KB_ENOGPU = -3
 
-STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5, "knn_exact": 6}
+STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5, "knn_exact": 6, "readgraph": 7}
 
 
 def KB_MODE_K(k):
@@ -53,6 +53,11 @@ SIGNATURES = {
     "kb_fasta_open": (c_int, [c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "kb_fasta_fill": (c_int, [_P, _P, _P, _P, _P, _P]),
     "kb_fasta_close": (c_int, [_P]),
+    "kb_eq_open": (c_int, [c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "kb_eq_fill": (c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "kb_eq_close": (c_int, [_P]),
+    "kb_readgraph_build": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, POINTER(c_int64)]),
+    "kb_readgraph_fetch": (c_int, [_P, _P, _P, _P, _P]),
     "kb_enable_timing": (c_int, [_P, c_int]),
     "kb_stage_ms": (c_int, [_P, c_int, POINTER(c_float), POINTER(c_int)]),
     "kb_launch_count": (c_int64, [_P]),

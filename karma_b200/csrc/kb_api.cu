@@ -86,6 +86,7 @@ extern "C" int kb_destroy(kb_ctx* c) {
     }
     cudaFree(c->d_k1_scratch);
     kb_free_exotic(c);
+    cudaFree(c->d_rg_a); cudaFree(c->d_rg_b); cudaFree(c->d_rg_w); cudaFree(c->d_rg_shared);
     free(c);
     return KB_OK;
 }

@@ -28,6 +28,8 @@ struct kb_ctx {
     uint64_t* d_ex_keys;            // unique keys
     int32_t* d_ex_row; int32_t* d_ex_keyidx; uint32_t* d_ex_cnt;
     int64_t ex_n_keys, ex_n_entries;
+    // read-graph edges of the last kb_readgraph_build (owned)
+    int32_t* d_rg_a; int32_t* d_rg_b; double* d_rg_w; uint64_t* d_rg_shared; int64_t rg_edges;
     // tensor-map encoder (driver entry point, resolved lazily)
     void* encode_tiled;
 };
