@@ -120,7 +120,8 @@ extern "C" int kb_stage_ms(kb_ctx* c, int which, float* mean_ms, int* n_launches
     const int n = c->ev_n[which] < KB_EV_RING ? c->ev_n[which] : KB_EV_RING;
     if (n_launches) *n_launches = n;
     *mean_ms = 0.f;
-    if (!c->ev0 || n == 0) { kb_set_error("stage %d was not timed", which); return KB_EINVAL; }
+    if (!c->ev0) { kb_set_error("timing is not enabled (kb_enable_timing)"); return KB_EINVAL; }
+    if (n == 0) return KB_OK;                                   // nothing recorded since the last read
     double sum = 0.0;
     for (int j = 0; j < n; ++j) {
         float ms = 0.f;
