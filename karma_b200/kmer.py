@@ -79,35 +79,36 @@ class KmerClustering:
         row, contig, length = args[0], args[1], args[2]
         return [(row, self.kmers[kmer], count / length) for kmer, count in contig.items()]
 
+    @staticmethod
+    def _first_token(names):
+        return [n.split(" ")[0] for n in names]
+
     def __fix_fasta_headers(self):
-        # kmer.py:94-106
-        self.unlabeled_cluster = [[name.split(" ")[0] for name in self.unlabeled_cluster[0]]]
-        renamed_cluster = []
-        for cluster in self.clusters:
-            renamed_cluster.append([name.split(" ")[0] for name in cluster])
-        assert len(renamed_cluster) == len(self.clusters), \
-            "Something went wrong while renaming fasta header. See if removing spaces from fasta headers solves the problem."
-        self.clusters = renamed_cluster
+        """Keep only the first space-delimited token of every contig name (kmer.py:94-106)."""
+        self.unlabeled_cluster = [self._first_token(self.unlabeled_cluster[0])]
+        self.clusters = [self._first_token(members) for members in self.clusters]
 
     def __save_groups_to_file(self):
-        # kmer.py:124-133: line 1 = unlabeled, then one cluster per line, tab separated
-        with open(self.output_file, "w") as cluster_writer:
-            cluster_writer.write("\t".join(self.unlabeled_cluster[0]) + "\n")
-            for cluster in self.clusters:
-                cluster_writer.write("\t".join(cluster) + "\n")
+        """cluster.txt (kmer.py:124-133): tab-separated names, one group per line, the unlabeled
+        group first."""
+        rows = [self.unlabeled_cluster[0]] + list(self.clusters)
+        with open(self.output_file, "w") as out:
+            out.writelines("\t".join(members) + "\n" for members in rows)
 
     def __read_clusters(self):
-        # kmer.py:135-144
-        with open(self.output_file, "r") as cluster_reader:
-            self.unlabeled_cluster = [cluster_reader.readline().rstrip("\n").split("\t")]
-            for line in cluster_reader:
-                self.clusters.append(line.rstrip("\n").split("\t"))
+        """Resume from a previous cluster.txt (kmer.py:135-144)."""
+        with open(self.output_file, "r") as src:
+            rows = [line.rstrip("\n").split("\t") for line in src]
+        if not rows:                                   # readline() on an empty file gives "" -> [""]
+            rows = [[""]]
+        self.unlabeled_cluster = [rows[0]]
+        self.clusters.extend(rows[1:])
 
-    def __write_eval_information(self, **kwargs):
-        # kmer.py:266-272
-        with open(f"{self.output_eval}", "w") as writer:
-            writer.write("\t".join(list(kwargs.keys())) + "\n")
-            writer.write("\t".join([str(a) for a in list(kwargs.values())]) + "\n")
+    def __write_eval_information(self, **fields):
+        """eval.txt (kmer.py:266-272): a header line and a value line, tab separated."""
+        with open(self.output_eval, "w") as out:
+            out.write("\t".join(fields) + "\n")
+            out.write("\t".join(str(v) for v in fields.values()) + "\n")
 
     # ------------------------------------------------------------------ GPU path
     def _pack(self):
@@ -165,42 +166,39 @@ class KmerClustering:
         return kmer_profile
 
     def run(self, neighbors, components, dist, r_state, min_cluster_size):
-        # kmer.py:274-325
+        """kmer.py:274-325: resume from cluster.txt if present, else profile (+ kNN) on the GPU,
+        UMAP, HDBSCAN, write cluster.txt / eval.txt."""
         if os.path.isfile(self.output_file):
             logger.info(f"Read from previous calculation: {self.output_file}")
             self.__read_clusters()
-        else:
-            logger.info("Calculate kmer profiles.")
-            kmer_profile = self.__calc_kmer_profile(n_neighbors=neighbors)
+            self.__fix_fasta_headers()
+            return
 
-            logger.info("Dimension reduction with UMAP.")
-            import umap
-            kwargs = dict(n_neighbors=neighbors, n_components=components, min_dist=dist, random_state=r_state)
-            try:
-                # umap-learn >= 0.5: hand over the exact graph (self in column 0, euclidean distances)
-                reducer = umap.UMAP(precomputed_knn=(self.knn_indices.astype(np.int64), self.knn_dists, None),
-                                    **kwargs).fit_transform(kmer_profile)
-            except TypeError:
-                # umap-learn 0.3.9 (conda/meta.yaml:15) has no such argument: unchanged call (kmer.py:285-290)
-                reducer = umap.UMAP(**kwargs).fit_transform(kmer_profile)
+        logger.info("Calculate kmer profiles.")
+        profile = self.__calc_kmer_profile(n_neighbors=neighbors)
 
-            logger.info(f"Perform clustering with HDBSCAN. (min_cluster_size: {min_cluster_size})")
-            import hdbscan
-            if min_cluster_size == 1:
-                clusterer = hdbscan.HDBSCAN(allow_single_cluster=True).fit(reducer)
-            else:
-                clusterer = hdbscan.HDBSCAN(min_cluster_size=min_cluster_size).fit(reducer)
+        logger.info("Dimension reduction with UMAP.")
+        import umap
+        umap_args = {"n_neighbors": neighbors, "n_components": components, "min_dist": dist, "random_state": r_state}
+        try:
+            # umap-learn >= 0.5 accepts the exact graph (self in column 0, euclidean distances)
+            graph = (self.knn_indices.astype(np.int64), self.knn_dists, None)
+            embedding = umap.UMAP(precomputed_knn=graph, **umap_args).fit_transform(profile)
+        except TypeError:
+            # umap-learn 0.3.9 (conda/meta.yaml:15) has no such argument: the call of kmer.py:285-290
+            embedding = umap.UMAP(**umap_args).fit_transform(profile)
 
-            self.clusters, self.unlabeled_cluster = self.__mask_list(self.sequences, clusterer.labels_)
+        logger.info(f"Perform clustering with HDBSCAN. (min_cluster_size: {min_cluster_size})")
+        import hdbscan
+        hdb_args = {"allow_single_cluster": True} if min_cluster_size == 1 else {"min_cluster_size": min_cluster_size}
+        clusterer = hdbscan.HDBSCAN(**hdb_args).fit(embedding)
+        labels = clusterer.labels_
 
-            self.__save_groups_to_file()
-
-            no_unlabeled = list(clusterer.labels_).count(-1)
-            no_groups = max(clusterer.labels_) + 1
-            mean_probability = np.mean(clusterer.probabilities_)
-            self.__write_eval_information(
-                kmer_size=self.kmer_size, n_neighbors=neighbors, n_components=components, min_dist=dist,
-                random_state=r_state, min_cluster_size=min_cluster_size, unlabeled=no_unlabeled,
-                no_groups=no_groups, mean_probability=mean_probability)
-
+        self.clusters, self.unlabeled_cluster = self.__mask_list(self.sequences, labels)
+        self.__save_groups_to_file()
+        self.__write_eval_information(
+            kmer_size=self.kmer_size, n_neighbors=neighbors, n_components=components, min_dist=dist,
+            random_state=r_state, min_cluster_size=min_cluster_size,
+            unlabeled=list(labels).count(-1), no_groups=max(labels) + 1,
+            mean_probability=np.mean(clusterer.probabilities_))
         self.__fix_fasta_headers()
