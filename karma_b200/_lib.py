@@ -5,8 +5,7 @@ fails, a KarmaB200Error is raised.
 """
 import ctypes
 import os
-from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64,
-                    c_uint8, c_uint32, c_uint64, c_void_p)
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkarma_b200.so")

@@ -142,7 +142,10 @@ class Engine:
         h = c_void_p()
         check(self.lib.kb_create(byref(h), self.device_index))
         self.ctx = h
-        self._ws = None
+        self._ws = None          # kNN workspace (grown on demand)
+        self._side = None        # D2H stream of the profile download
+        self._up = None          # H2D stream of the chunked upload
+        self._host = {}          # reusable pinned result buffers
         self._bind_stream()
 
     def close(self):
@@ -174,7 +177,7 @@ class Engine:
 
     # ---- host-side plumbing -------------------------------------------------------
     def side_stream(self):
-        if getattr(self, "_side", None) is None:
+        if self._side is None:
             self._side = torch.cuda.Stream(self.device)
         return self._side
 
@@ -183,7 +186,7 @@ class Engine:
         engine and overwritten by the next call."""
         if not reuse:
             return torch.empty(shape, dtype=dtype, pin_memory=True)
-        cache = self.__dict__.setdefault("_host", {})
+        cache = self._host
         t = cache.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(shape, dtype=dtype, pin_memory=True)
@@ -218,8 +221,9 @@ class Engine:
         ho = offsets if isinstance(offsets, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int64))
         hk = key_len if isinstance(key_len, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(key_len, dtype=np.int32))
         main = torch.cuda.current_stream(self.device)
-        up = self.__dict__.setdefault("_up", None) or torch.cuda.Stream(self.device)
-        self._up = up
+        if self._up is None:
+            self._up = torch.cuda.Stream(self.device)
+        up = self._up
         up.wait_stream(main)
         chunks = []
         with torch.cuda.stream(up):

@@ -5,7 +5,6 @@ Returns the same ``OrderedDict{">name": sequence}`` karma.py builds, as a ``Pack
 that also carries the packed buffers (bases, offsets, key_len), so that
 ``KmerClustering`` hands them to the GPU without re-joining a million Python strings.
 """
-import ctypes
 from collections import OrderedDict
 from ctypes import byref, c_int64, c_void_p
 
