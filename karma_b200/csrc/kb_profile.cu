@@ -45,31 +45,41 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
         const double len = (double)key_len[row];
         unsigned long long sq = 0;
         uint32_t mx = 0;
-        for (int c = 4 * lane; c < cols4; c += 128) {
-            const uint4 v = *reinterpret_cast<const uint4*>(src + c);
-            sq += (unsigned long long)v.x * v.x + (unsigned long long)v.y * v.y +
-                  (unsigned long long)v.z * v.z + (unsigned long long)v.w * v.w;
-            mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
-            if (profile) {
-                double2 a, b;
-                a.x = v.x ? (double)v.x / len : 0.0;
-                a.y = v.y ? (double)v.y / len : 0.0;
-                b.x = v.z ? (double)v.z / len : 0.0;
-                b.y = v.w ? (double)v.w / len : 0.0;
-                double2* p = reinterpret_cast<double2*>(profile + row * ld_profile + c);
-                if (((ld_profile & 1) == 0)) { p[0] = a; p[1] = b; }
-                else {
-                    double* q = profile + row * ld_profile + c;
-                    q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+        // two 128-bit loads in flight per lane before anything is stored
+        for (int c = 4 * lane; c < cols4; c += 256) {
+            const bool two = c + 128 < cols4;
+            const uint4 v0 = __ldcs(reinterpret_cast<const uint4*>(src + c));
+            const uint4 v1 = two ? __ldcs(reinterpret_cast<const uint4*>(src + c + 128)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1 && !two) break;
+                const uint4 v = half ? v1 : v0;
+                const int cc = c + 128 * half;
+                sq += (unsigned long long)v.x * v.x + (unsigned long long)v.y * v.y +
+                      (unsigned long long)v.z * v.z + (unsigned long long)v.w * v.w;
+                mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+                if (profile) {
+                    double2 a, b;
+                    a.x = v.x ? (double)v.x / len : 0.0;
+                    a.y = v.y ? (double)v.y / len : 0.0;
+                    b.x = v.z ? (double)v.z / len : 0.0;
+                    b.y = v.w ? (double)v.w / len : 0.0;
+                    if (((ld_profile & 1) == 0)) {
+                        double2* p = reinterpret_cast<double2*>(profile + row * ld_profile + cc);
+                        __stcs(p, a); __stcs(p + 1, b);
+                    } else {
+                        double* q = profile + row * ld_profile + cc;
+                        q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+                    }
                 }
-            }
-            if (operand) {
-                const __half2 h0 = __floats2half2_rn((float)min(v.x, 2048u), (float)min(v.y, 2048u));
-                const __half2 h1 = __floats2half2_rn((float)min(v.z, 2048u), (float)min(v.w, 2048u));
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(operand + row * ld_operand + c) = pk;
+                if (operand) {
+                    const __half2 h0 = __floats2half2_rn((float)min(v.x, 2048u), (float)min(v.y, 2048u));
+                    const __half2 h1 = __floats2half2_rn((float)min(v.z, 2048u), (float)min(v.w, 2048u));
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                    *reinterpret_cast<uint2*>(operand + row * ld_operand + cc) = pk;
+                }
             }
         }
         // tail columns (cols % 4) and operand zero padding
