@@ -18,7 +18,8 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64
     if (k < 1 || nq < 1 || nk < 1 || k > nk) { kb_set_error("kNN: need 1 <= k <= nk and nq >= 1"); return KB_EINVAL; }
     if (k > 24) { kb_set_error("kNN: n_neighbors > 24 not built (candidate lists are <= 32 wide)"); return KB_EUNSUPPORTED; }
     p->impl = impl;
-    p->kp = (k <= 4) ? 8 : (k <= 10 ? 16 : 32);
+    // candidates kept per (row, split): k plus a margin of >= 6 against fp32 ranking noise, in steps of 8
+    p->kp = (k <= 2) ? 8 : (k <= 10 ? 16 : (k <= 18 ? 24 : 32));
     if (impl == KB_KNN_TC) { p->bm = 128; p->bn = 256; }
     else { p->bm = 64; p->bn = 64; }
     p->m_blocks = (nq + p->bm - 1) / p->bm;
@@ -30,7 +31,8 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64
     const int64_t groups = (p->m_blocks + cl - 1) / cl;
     const int64_t workers = impl == KB_KNN_TC ? (sm_count / cl > 0 ? sm_count / cl : 1) : (int64_t)sm_count * 2;
     int64_t want = 1; double best_cost = 1e300;
-    for (int64_t s_try = 1; s_try <= 32 && s_try <= p->n_tiles; ++s_try) {
+    const int64_t max_splits = 512 / p->kp < 32 ? 512 / p->kp : 32;   // K5 merges at most 512 candidates per row
+    for (int64_t s_try = 1; s_try <= max_splits && s_try <= p->n_tiles; ++s_try) {
         const int64_t rounds = (groups * s_try + workers - 1) / workers;
         const int64_t per_unit = (p->n_tiles + s_try - 1) / s_try;
         const double cost = (double)rounds * ((double)per_unit + 0.5);
@@ -39,6 +41,7 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64
     if (const char* f = getenv("KB_KNN_SPLITS")) {              // experiments only
         const int64_t v = atoll(f);
         if (v >= 1) want = v < p->n_tiles ? v : p->n_tiles;
+        if (want > max_splits) want = max_splits;
     }
     p->splits = (int)want;
     p->nk_pad = p->n_tiles * p->bn;
@@ -506,6 +509,7 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
             switch (p.kp) {
                 case 8: rc = run_simt<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
                 case 16: rc = run_simt<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
+                case 24: rc = run_simt<24>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
                 default: rc = run_simt<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
             }
         }
@@ -517,6 +521,7 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
         switch (p.kp) {
             case 8: rc = run_exact<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
             case 16: rc = run_exact<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
+            case 24: rc = run_exact<24>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
             default: rc = run_exact<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
         }
         if (rc) return rc;
@@ -526,6 +531,7 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
         switch (p.kp) {
             case 8: rc = run_rerank<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
             case 16: rc = run_rerank<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
+            case 24: rc = run_rerank<24>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
             default: rc = run_rerank<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
         }
     }

@@ -465,6 +465,7 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
     switch (p.kp) {
         case 8: return launch_tc_kp<8>(ctx, tmap, prm);
         case 16: return launch_tc_kp<16>(ctx, tmap, prm);
+        case 24: return launch_tc_kp<24>(ctx, tmap, prm);
         default: return launch_tc_kp<32>(ctx, tmap, prm);
     }
 }
