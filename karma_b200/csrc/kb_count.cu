@@ -408,9 +408,12 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
     if constexpr (WARP_PER_CONTIG) {
         auto k1 = k1_count_warp<KA, KB, PALB, SORTED, WARPS>;
         const size_t smem = (size_t)(COLS + 32) * sizeof(uint32_t) * WARPS + (SORTED ? 2048 : 0);
-        KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, WARPS * 32, smem));
+        static int per_sm_cache[16] = {0};                     // per device: attribute set + occupancy known
+        int& per_sm = per_sm_cache[ctx->device & 15];
+        if (per_sm == 0) {
+            KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, WARPS * 32, smem));
+        }
         if (per_sm < 1) { kb_set_error("k1_count_warp does not fit on an SM"); return KB_ECUDA; }
         int64_t grid = (int64_t)ctx->sm_count * per_sm;         // persistent: one resident wave
         const int64_t want = (n + WARPS - 1) / WARPS;
@@ -423,9 +426,12 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         ctx->launches++;
     } else {
         auto k1 = k1_count_cta<KA, KB, PALB, SORTED, THREADS>;
-        KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
-        int per_sm = 0;
-        KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, THREADS, smem_one));
+        static int per_sm_cache[16] = {0};
+        int& per_sm = per_sm_cache[ctx->device & 15];
+        if (per_sm == 0) {
+            KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
+            KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, THREADS, smem_one));
+        }
         if (per_sm < 1) { kb_set_error("k1_count_cta does not fit on an SM"); return KB_ECUDA; }
         int64_t grid = (int64_t)ctx->sm_count * per_sm;
         if (grid > n) grid = n;
@@ -439,7 +445,11 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
     KB_CUDA(cudaGetLastError());
     {
         auto k1l = k1_count_long<KA, KB, PALB, SORTED, THREADS>;
-        KB_CUDA(cudaFuncSetAttribute(k1l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
+        static bool attr_set[16] = {false};
+        if (!attr_set[ctx->device & 15]) {
+            KB_CUDA(cudaFuncSetAttribute(k1l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
+            attr_set[ctx->device & 15] = true;
+        }
         KbTimer t(ctx, 1);
         k1l<<<(unsigned)(ctx->sm_count * 2), THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, d_counts, ld,
                                                                               d_exotic, d_presence,

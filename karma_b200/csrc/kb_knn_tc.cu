@@ -393,7 +393,11 @@ template <int KP, int STAGES, int CL>
 int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
     using L = Smem<KP, STAGES>;
     auto kern = k4_tc<KP, STAGES, CL>;
-    KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    static bool attr_set[16] = {false};                        // per template instance and device
+    if (!attr_set[ctx->device & 15]) {
+        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set[ctx->device & 15] = true;
+    }
     const int64_t n_units = ((prm.m_blocks + CL - 1) / CL) * prm.splits;
     int64_t clusters = ctx->sm_count / CL;
     if (clusters > n_units) clusters = n_units;
