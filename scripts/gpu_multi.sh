@@ -8,6 +8,8 @@ timeout 600 $TR --nproc-per-node $N --master-port 29511 scripts/multi_gpu_check.
 timeout 600 $TR --nproc-per-node $N --master-port 29512 scripts/multi_gpu_check.py --contigs 3000 --neighbors 2 --synth S2 > gpurun_out/multi_parity2.log 2>&1; echo "parity k2 rc=$?"
 timeout 600 $TR --nproc-per-node $N --master-port 29513 scripts/multi_gpu_check.py --contigs 401 --neighbors 4 --synth S3 > gpurun_out/multi_parity3.log 2>&1; echo "parity S3 (flagged rows) rc=$?"
 grep -h "MULTI_GPU_PARITY" gpurun_out/multi_parity3.log | tail -2
+timeout 600 $TR --nproc-per-node $N --master-port 29514 scripts/multi_gpu_check.py --contigs 6 --neighbors 3 --synth S0 --exotic > gpurun_out/multi_parity4.log 2>&1; echo "parity exotic+compaction rc=$?"
+grep -h "MULTI_GPU_PARITY" gpurun_out/multi_parity4.log | tail -2
 grep -h "MULTI_GPU_PARITY\|rows \[" gpurun_out/multi_parity.log gpurun_out/multi_parity2.log | tail -20
 for g in 1 2 4 8; do
   if [ $g -le $N ]; then

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--neighbors", type=int, default=15)
     ap.add_argument("--synth", default="S1")
     ap.add_argument("--kmer", default="5p6")
+    ap.add_argument("--exotic", action="store_true", help="inject N / lowercase bases into contigs of different ranks")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -34,9 +35,14 @@ def main():
     eng = Engine(local)
     kmer = int(a.kmer) if a.kmer.isdigit() else a.kmer
     asm = synth.make(a.synth, a.contigs)
-    if a.kmer == "5p6":
-        # make the dictionary non-trivial: drop every contig's chance to hold some 5-mers on one rank only
-        pass
+    if a.exotic:
+        # windows with non-ACGT bytes get string-keyed columns (kmer.py has no alphabet); put different
+        # ones on different ranks so that the key union and the column merge cross the rank boundary
+        bases = asm.bases.copy()
+        for i, (pos, ch) in zip((1, asm.n // 2 + 1, asm.n - 1), ((20, b"N"), (33, b"n"), (7, b"R"))):
+            bases[asm.offsets[i] + pos] = ch[0]
+            bases[asm.offsets[i] + pos + 9] = ord("a")
+        asm = synth.Assembly(bases, asm.offsets, asm.gene, asm.iso)
     lo, hi, per = shard_bounds(asm.n, world, rank)
     shard = asm.slice(lo, hi)
     res = profile_and_knn(eng, shard.bases, shard.offsets, shard.key_len, kmer, n_neighbors=a.neighbors,
