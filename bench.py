@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--shard-gen", action="store_true", help="each rank synthesises only its own row shard")
+    ap.add_argument("--profile-host", action="store_true", help="cProfile the timed loop on rank 0 (diagnostics)")
     return ap.parse_args()
 
 
@@ -319,10 +320,19 @@ def run_ours(a):
     for st in ("count", "normalise", "knn_gemm", "rerank"):
         eng.stage_ms(st)                                    # drop the warm-up launches
     barrier()
+    prof = None
+    if a.profile_host and rank == 0:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     ev0.record()
     for _ in range(a.steps):
         device_step()
     ev1.record()
+    if prof is not None:
+        prof.disable()
+        import pstats
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(28)
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = eng.launches() - launches0

@@ -146,6 +146,7 @@ class Engine:
         self._side = None        # D2H stream of the profile download
         self._up = None          # H2D stream of the chunked upload
         self._host = {}          # reusable pinned result buffers
+        self._hold_stream = False
         self._bind_stream()
 
     def close(self):
@@ -160,6 +161,9 @@ class Engine:
             pass
 
     def _bind_stream(self):
+        """Point the library at torch's current stream (skipped while a pass holds the binding)."""
+        if self._hold_stream:
+            return
         check(self.lib.kb_set_stream(self.ctx, c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
     # ---- timing / accounting -------------------------------------------------
@@ -385,9 +389,20 @@ def all_gather_rows(t, group):
     return out
 
 
-def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
-                want_profile=True, group=None, rank=0, world=1, n_total=None, gather_lists=False, bufs=None,
-                on_profile=None, optimistic=True, row0=0, chunks=None):
+def device_pass(engine, *args, **kwargs):
+    """See _device_pass.  The stream binding of the library is taken once for the whole pass."""
+    engine._bind_stream()
+    held = engine._hold_stream
+    engine._hold_stream = True
+    try:
+        return _device_pass(engine, *args, **kwargs)
+    finally:
+        engine._hold_stream = held
+
+
+def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
+                 want_profile=True, group=None, rank=0, world=1, n_total=None, gather_lists=False, bufs=None,
+                 on_profile=None, optimistic=True, row0=0, chunks=None):
     """The hot path on device-resident inputs: K1 -> column dictionary (-> K1x/K2) -> K3
     [-> all-gather of the operand shards -> K4 (-> K4x) -> K5].  Returns device tensors plus
     the column list.
@@ -543,9 +558,9 @@ def device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_nei
         if n_neighbors is not None and (flags_or & 3):
             redo = True
         if redo:
-            return device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors, impl, want_profile,
-                               group, rank, world, n_total, gather_lists, bufs, on_profile, optimistic=False, row0=row0,
-                               chunks=None)
+            return _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors, impl, want_profile,
+                                group, rank, world, n_total, gather_lists, bufs, on_profile, optimistic=False, row0=row0,
+                                chunks=None)
     if flags_or & 4:
         # a contig shorter than k (kmer.py:250-258): report the first such row of this rank
         own = rowmeta[:n, 3].cpu().numpy()
