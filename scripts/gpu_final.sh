@@ -7,4 +7,4 @@ timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 > gpurun_out/pyt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log | cut -c1-200
 timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "bench reference rc=$?"
 timeout 600 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
-bash scripts/gpu_profile.sh > gpurun_out/prof.txt 2>&1; grep -E "rc=" gpurun_out/prof.txt
+if [ "${KB_WITH_NCU:-0}" = "1" ]; then bash scripts/gpu_profile.sh > gpurun_out/prof.txt 2>&1; grep -E "rc=" gpurun_out/prof.txt; fi
