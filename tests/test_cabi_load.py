@@ -37,6 +37,20 @@ def test_exports_every_declared_symbol(lib):
         assert hasattr(raw, name), name
 
 
+def test_ctypes_signatures_match_header_arity():
+    """Every prototype in include/karma_b200.h must have as many parameters as its ctypes binding."""
+    from karma_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "karma_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"KB_API\s+[\w\s\*]+?\b(kb_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(_lib.SIGNATURES[name][1]), "%s: header has %d parameters, ctypes binding %d" % (
+            name, n, len(_lib.SIGNATURES[name][1]))
+
+
 def test_pure_host_entry_points(lib):
     from karma_b200 import _lib
     assert lib.kb_version() >= 100
