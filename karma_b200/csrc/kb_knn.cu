@@ -27,7 +27,12 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64
     // Splits: units = (query-block groups) x S are dealt round-robin to the resident CTAs (tensor path:
     // CTA pairs, so sm_count/2 workers and groups of 2 blocks).  Pick S in [1,32] minimising the makespan
     // rounds(S) * tiles_per_unit(S), charging half a tile per unit for list setup and write-back.
-    const int64_t cl = (impl == KB_KNN_TC && p->m_blocks >= 2) ? 2 : 1;
+    int64_t cl = (impl == KB_KNN_TC && p->m_blocks >= 2) ? 2 : 1;
+    if (const char* f = getenv("KB_KNN_CLUSTER")) {             // experiments only: 1, 2 or 4 CTAs share every key tile
+        const int v = atoi(f);
+        if (impl == KB_KNN_TC && (v == 1 || v == 2 || v == 4) && p->m_blocks >= v) cl = v;
+    }
+    p->cl = (int)cl;
     const int64_t groups = (p->m_blocks + cl - 1) / cl;
     const int64_t workers = impl == KB_KNN_TC ? (sm_count / cl > 0 ? sm_count / cl : 1) : (int64_t)sm_count * 2;
     int64_t want = 1; double best_cost = 1e300;

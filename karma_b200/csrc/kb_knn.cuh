@@ -12,6 +12,7 @@ struct KbKnnPlan {
     int64_t m_blocks;    // ceil(nq / bm)
     int64_t n_tiles;     // ceil(nk / bn)
     int splits;          // S
+    int cl;              // tensor path: CTAs per cluster sharing one key-tile stream (1, 2 or 4)
     int64_t nk_pad;      // colmeta length (multiple of bn)
     // workspace offsets (bytes)
     int64_t off_colmeta, off_score, off_idx, off_rowthr, off_xidx, off_xd2, total;

@@ -196,8 +196,10 @@ struct Smem {
 // traffic per tile from 384 to 256 rows (the v2 profile had the L2 at 73 % of peak).
 template <int KP, int STAGES, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
     using L = Smem<KP, STAGES>;
+    constexpr int B_PART_ROWS = CL == 1 ? 128 : BN / CL;       // rows of the key tile one TMA brings (box of tmap_b)
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,6 +215,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         // a stage is free again once the MMAs of EVERY CTA that receives multicast data into
         // it have retired: each CTA's commit arrives on all CL empty barriers
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
@@ -251,11 +254,11 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                         mbar_expect_tx(fb, STAGE_BYTES);
                         tma_load_2d(sa, &tmap, kb * BK, arow, fb);
                         if constexpr (CL == 1) {
-                            tma_load_2d(sa + A_BYTES, &tmap, kb * BK, brow, fb);
-                            tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, kb * BK, brow + 128, fb);
+                            tma_load_2d(sa + A_BYTES, &tmap_b, kb * BK, brow, fb);
+                            tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap_b, kb * BK, brow + 128, fb);
                         } else {
-                            // my half of B goes to the same smem offset (and full barrier) of both CTAs
-                            tma_load_2d_mc(sa + A_BYTES + cta_rank * (B_BYTES / 2), &tmap, kb * BK, brow + 128 * cta_rank, fb, (uint16_t)0x3);
+                            // my 1/CL of B goes to the same smem offset (and full barrier) of every CTA of the cluster
+                            tma_load_2d_mc(sa + A_BYTES + cta_rank * (B_BYTES / CL), &tmap_b, kb * BK, brow + B_PART_ROWS * cta_rank, fb, CL_MASK);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -286,7 +289,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                         }
                         // frees the smem stage (here and in the peer CTA) when these MMAs retire
                         if constexpr (CL == 1) umma_commit(bar_empty + 8 * stage);
-                        else umma_commit_mc(bar_empty + 8 * stage, (uint16_t)0x3);
+                        else umma_commit_mc(bar_empty + 8 * stage, CL_MASK);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(bar_tfull + 8 * acc);                // accumulator ready for the epilogue
@@ -385,30 +388,281 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     }
 }
 
+// =====================================================================================
+// k4_tc2: the same unit/epilogue structure with ONE 2-CTA MMA per CTA pair
+// (tcgen05.mma.cta_group::2, M=256 N=256 K=16).  Each CTA keeps its 128 query rows (A) and
+// HALF of the key tile (128 B rows) in shared memory: 32 KB per stage instead of 48 KB, so
+// the ring is 6 deep, and the tensor core reads B once for both SMs.  The leader CTA (cluster
+// rank 0) issues the MMAs; every TMA of either CTA signals the leader's "full" barrier
+// (.cta_group::2 TMA with the peer-masked barrier address); the leader's commits are multicast
+// to both CTAs' "stage empty" and "accumulator full" barriers; both CTAs' epilogue warps arrive
+// on the leader's "accumulator empty" barrier.  Opt-in (KB_KNN_MMA2=1) until it has been timed.
+// =====================================================================================
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the cluster-rank bit of a shared address: the even CTA
+constexpr int STAGE2_BYTES = A_BYTES + B_BYTES / 2;  // 32 KB per CTA and stage
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) {   // arrive on CTA `rank`'s copy of `bar`
+    asm volatile("{\n\t.reg .b32 ra;\n\t"
+                 "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
+}
+
+template <int KP, int STAGES>
+struct Smem2 {
+    static constexpr int OFF_STAGES = 0;
+    static constexpr int OFF_LIST_S = STAGES * STAGE2_BYTES;
+    static constexpr int OFF_LIST_I = OFF_LIST_S + KP * BM * 4;
+    static constexpr int OFF_COLMETA = OFF_LIST_I + KP * BM * 4;
+    static constexpr int OFF_BARS = OFF_COLMETA + BN * 8;
+    static constexpr int OFF_TMEM_SLOT = OFF_BARS + (2 * STAGES + 4) * 8;
+    static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
+};
+
+template <int KP, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    using L = Smem2<KP, STAGES>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && (sbase & 1023u)) {
+        printf("kb_knn_tc2: dynamic shared memory is not 1024-byte aligned (0x%x)\n", sbase);
+        __trap();
+    }
+    const uint32_t bar_full = sbase + L::OFF_BARS;            // used in the leader CTA only
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + STAGES * 8;
+    const uint32_t bar_tempty = bar_tfull + 2 * 8;             // used in the leader CTA only
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L::OFF_TMEM_SLOT);
+    const int cta_rank = (int)cluster_ctarank();
+    const bool leader = cta_rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        // accumulator empty: 4 epilogue warps of each of the two CTAs
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {                                          // both CTAs, same warp id
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t n_units = ((p.m_blocks + 1) / 2) * p.splits;
+    const int64_t u0 = blockIdx.x / 2, ustep = gridDim.x / 2;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t u = u0; u < n_units; u += ustep) {
+                const Unit un(p, u, 2, cta_rank);
+                const int32_t arow = (int32_t)(p.q_row0 + un.mb * BM);
+                for (int64_t i = 0; i < un.cnt; ++i) {
+                    const int32_t brow = (int32_t)(un.tile(i) * BN) + 128 * cta_rank;   // my half of the key tile
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
+                        const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE2_BYTES;
+                        const uint32_t fb = (bar_full + 8 * stage) & PEER_MASK;          // the leader's barrier
+                        if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * STAGE2_BYTES);   // both CTAs' bytes
+                        tma_load_2d_2sm(sa, &tmap, kb * BK, arow, fb);
+                        tma_load_2d_2sm(sa + A_BYTES, &tmap, kb * BK, brow, fb);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t u = u0; u < n_units; u += ustep) {
+                const Unit un(p, u, 2, 0);
+                for (int64_t i = 0; i < un.cnt; ++i) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 12);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(bar_full + 8 * stage, phase, 13);
+                        tc_fence_after();
+                        const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE2_BYTES;
+                        const uint64_t adesc = make_smem_desc(sa);
+                        const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC2, (kb | k) != 0);
+                        umma_commit_2sm_mc(bar_empty + 8 * stage, (uint16_t)0x3);   // both CTAs' stage is free
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_2sm_mc(bar_tfull + 8 * acc, (uint16_t)0x3);          // both CTAs' epilogues may read
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: warps 2..5 of both CTAs (each its own 128 rows) =================
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const int et = threadIdx.x - 64;
+        KbRowList<KP, BM> list(reinterpret_cast<float*>(smem + L::OFF_LIST_S),
+                               reinterpret_cast<int32_t*>(smem + L::OFF_LIST_I));
+        const float4* cm4 = reinterpret_cast<const float4*>(smem + L::OFF_COLMETA);
+        float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t u = u0; u < n_units; u += ustep) {
+            const Unit un(p, u, 2, cta_rank);
+            const int64_t q = un.mb * BM + r;
+            const bool live = q < p.nq;
+            const float li = live ? (float)p.rowmeta[p.q_row0 + q].key_len : 1.f;
+            list.init(r);
+            float thr = __int_as_float(0x7f800000);
+            for (int64_t i = 0; i < un.cnt; ++i) {
+                const int64_t n0 = un.tile(i) * BN;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                cm_s[et] = p.colmeta[n0 + et];
+                cm_s[et + 128] = p.colmeta[n0 + et + 128];
+                if (live) thr = fminf(thr, key2f(__ldcg(p.row_thr + q)));
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(bar_tfull + 8 * acc, acc_phase, 14);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    float sc[32];
+                    float m0 = thr, m1 = thr, m2 = thr, m3 = thr;
+#pragma unroll
+                    for (int x = 0; x < 32; x += 2) {
+                        const float4 cm = cm4[c * 16 + (x >> 1)];
+                        sc[x] = fmaf(__uint_as_float(v[x]), cm.x, li * cm.y);
+                        sc[x + 1] = fmaf(__uint_as_float(v[x + 1]), cm.z, li * cm.w);
+                    }
+#pragma unroll
+                    for (int x = 0; x < 32; x += 4) {
+                        m0 = fminf(m0, sc[x]); m1 = fminf(m1, sc[x + 1]);
+                        m2 = fminf(m2, sc[x + 2]); m3 = fminf(m3, sc[x + 3]);
+                    }
+                    if (fminf(fminf(m0, m1), fminf(m2, m3)) < thr) {
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            if (sc[x] < thr) {
+                                list.insert(r, sc[x], (int32_t)(n0 + c * 32 + x));
+                                thr = fminf(thr, list.bound);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_rank(bar_tempty + 8 * acc, 0);   // the leader's barrier
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (live && list.bound < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(list.bound));
+            }
+            if (live) {
+                const int64_t base = (q * p.splits + un.s) * KP;
+#pragma unroll
+                for (int e = 0; e < KP; ++e) {
+                    p.cand_score[base + e] = list.s[e * BM + r];
+                    p.cand_idx[base + e] = list.i[e * BM + r];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <int KP, int STAGES, int CL>
-int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
+int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, const TcParams& prm) {
     using L = Smem<KP, STAGES>;
     auto kern = k4_tc<KP, STAGES, CL>;
-    static bool attr_set[16] = {false};                        // per template instance and device
-    if (!attr_set[ctx->device & 15]) {
-        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set[ctx->device & 15] = true;
-    }
-    const int64_t n_units = ((prm.m_blocks + CL - 1) / CL) * prm.splits;
-    int64_t clusters = ctx->sm_count / CL;
-    if (clusters > n_units) clusters = n_units;
+    static int max_clusters[16] = {0};                         // per template instance and device
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * CL));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (!max_clusters[ctx->device & 15]) {
+        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        int fit = ctx->sm_count / CL;
+        if (CL > 2) {                                          // clusters live inside one GPC: fewer than sm_count/CL may fit
+            cfg.gridDim = dim3((unsigned)(ctx->sm_count / CL * CL));
+            KB_CUDA(cudaOccupancyMaxActiveClusters(&fit, kern, &cfg));
+            if (fit < 1) { kb_set_error("kNN: no cluster of %d CTAs fits on this device", CL); return KB_ECUDA; }
+            if (fit > ctx->sm_count / CL) fit = ctx->sm_count / CL;
+        }
+        max_clusters[ctx->device & 15] = fit;
+    }
+    const int64_t n_units = ((prm.m_blocks + CL - 1) / CL) * prm.splits;
+    int64_t clusters = max_clusters[ctx->device & 15];
+    if (clusters > n_units) clusters = n_units;
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    KB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, tmap_b, prm));
+    ctx->launches++;
+    KB_CUDA(cudaGetLastError());
+    return KB_OK;
+}
+
+template <int KP>
+int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
+    using L = Smem2<KP, 6>;
+    auto kern = k4_tc2<KP, 6>;
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set[ctx->device & 15] = true;
+    }
+    const int64_t n_units = ((prm.m_blocks + 1) / 2) * prm.splits;
+    int64_t clusters = ctx->sm_count / 2;
+    if (clusters > n_units) clusters = n_units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * 2));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     KB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, prm));
     ctx->launches++;
@@ -417,12 +671,14 @@ int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
 }
 
 template <int KP>
-int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
+int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, int cl, const TcParams& prm) {
+    if (const char* m2 = getenv("KB_KNN_MMA2")) {              // opt-in: one 2-CTA MMA per CTA pair
+        if (atoi(m2) == 1 && cl == 2) return launch_tc2<KP>(ctx, tmap, prm);
+    }
     // pairs of query blocks share B through multicast whenever there are at least two blocks
-    const char* force = getenv("KB_KNN_CLUSTER");
-    const int cl = force ? atoi(force) : (prm.m_blocks >= 2 ? 2 : 1);
-    if (cl == 2) return launch_tc<KP, 4, 2>(ctx, tmap, prm);
-    return launch_tc<KP, 4, 1>(ctx, tmap, prm);
+    if (cl == 4) return launch_tc<KP, 4, 4>(ctx, tmap, tmap_b, prm);
+    if (cl == 2) return launch_tc<KP, 4, 2>(ctx, tmap, tmap_b, prm);
+    return launch_tc<KP, 4, 1>(ctx, tmap, tmap_b, prm);
 }
 
 }  // namespace
@@ -457,6 +713,16 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
                                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { kb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return KB_ECUDA; }
+    // key tiles arrive in parts of 128 rows (1 or 2 CTAs per cluster) or 64 rows (4 CTAs)
+    CUtensorMap tmap_b = tmap;
+    if (p.cl == 4) {
+        const cuuint32_t box_b[2] = {BK, (cuuint32_t)(BN / 4)};
+        cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_operand),
+                                               gdim, gstride, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { kb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return KB_ECUDA; }
+    }
     TcParams prm;
     prm.nk = nk; prm.q_row0 = q_row0; prm.nq = nq;
     prm.m_blocks = p.m_blocks; prm.n_tiles = p.n_tiles; prm.splits = p.splits;
@@ -467,9 +733,9 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
     prm.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
     prm.row_thr = reinterpret_cast<int32_t*>(ws + p.off_rowthr);
     switch (p.kp) {
-        case 8: return launch_tc_kp<8>(ctx, tmap, prm);
-        case 16: return launch_tc_kp<16>(ctx, tmap, prm);
-        case 24: return launch_tc_kp<24>(ctx, tmap, prm);
-        default: return launch_tc_kp<32>(ctx, tmap, prm);
+        case 8: return launch_tc_kp<8>(ctx, tmap, tmap_b, p.cl, prm);
+        case 16: return launch_tc_kp<16>(ctx, tmap, tmap_b, p.cl, prm);
+        case 24: return launch_tc_kp<24>(ctx, tmap, tmap_b, p.cl, prm);
+        default: return launch_tc_kp<32>(ctx, tmap, tmap_b, p.cl, prm);
     }
 }
