@@ -405,7 +405,7 @@ def run_ours(a):
                          ((total_bases_all + n_total * d_cols * (4 + 8 + 2)) / 1e9)},
         "clocks": clocks, "gpu_launches": int(launches),
         "stage_ms": {"count": count_ms, "normalise": norm_ms, "knn_gemm": gemm_ms, "rerank": rerank_ms},
-        "roofline": {"bound": "tensor", "kernel": "k4_tc (distance GEMM + fused top-k)" if a.knn_impl == "tc" else "k4_simt",
+        "roofline": {"bound": "tensor", "kernel": "k4_tc2 (distance GEMM, 2-CTA tcgen05 MMA + fused top-k)" if a.knn_impl == "tc" else "k4_simt",
                      "achieved": ach_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach_tf / pk["tflops"],
                      "traffic": (ncu_traffic("k4_tc") or {}).get("bytes"), "traffic_source": (ncu_traffic("k4_tc") or {}).get("source"),
                      "peak_source": pk["source"] + ", bf16 burst; sustained %s" % pk["tflops_sustained"],

@@ -396,7 +396,8 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
 // rank 0) issues the MMAs; every TMA of either CTA signals the leader's "full" barrier
 // (.cta_group::2 TMA with the peer-masked barrier address); the leader's commits are multicast
 // to both CTAs' "stage empty" and "accumulator full" barriers; both CTAs' epilogue warps arrive
-// on the leader's "accumulator empty" barrier.  Opt-in (KB_KNN_MMA2=1) until it has been timed.
+// on the leader's "accumulator empty" barrier.  Default for CTA pairs: +0.4 % at 1088 columns, +10 % at 5120
+// (profiles/r01/k4_variants.md); KB_KNN_MMA2=0 selects k4_tc<.,.,2> instead.
 // =====================================================================================
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the cluster-rank bit of a shared address: the even CTA
 constexpr int STAGE2_BYTES = A_BYTES + B_BYTES / 2;  // 32 KB per CTA and stage
@@ -672,10 +673,9 @@ int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
 
 template <int KP>
 int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, int cl, const TcParams& prm) {
-    if (const char* m2 = getenv("KB_KNN_MMA2")) {              // opt-in: one 2-CTA MMA per CTA pair
-        if (atoi(m2) == 1 && cl == 2) return launch_tc2<KP>(ctx, tmap, prm);
-    }
-    // pairs of query blocks share B through multicast whenever there are at least two blocks
+    // CTA pairs run one 2-CTA MMA (k4_tc2) unless KB_KNN_MMA2=0 asks for the two-MMA multicast kernel (experiments)
+    const char* m2 = getenv("KB_KNN_MMA2");
+    if (cl == 2 && !(m2 && atoi(m2) == 0)) return launch_tc2<KP>(ctx, tmap, prm);
     if (cl == 4) return launch_tc<KP, 4, 4>(ctx, tmap, tmap_b, prm);
     if (cl == 2) return launch_tc<KP, 4, 2>(ctx, tmap, tmap_b, prm);
     return launch_tc<KP, 4, 1>(ctx, tmap, tmap_b, prm);
