@@ -234,12 +234,35 @@ KB_API int kb_readgraph_build(kb_ctx* ctx, int64_t n_contigs, int64_t n_classes,
                        uint64_t* d_totals, int64_t* n_edges);
 KB_API int kb_readgraph_fetch(kb_ctx* ctx, int32_t* h_a, int32_t* h_b, double* h_weight, uint64_t* h_shared);
 
+/* ---- connection weights between groups of contigs (follows the read graph) ----
+ * Replaces the itertools.product loops of calc_connections_between_mcl_subclusters
+ * (karma.py:103-118) and ReadGraph.calc_distance_between_subgraphs (read_graph.py:359-373).
+ * Inputs (device): the undirected edge list (every edge once) with float64 weights, and per node
+ * a ROW role (group, position in that group's node list) and a COLUMN role, -1 = none.  For every
+ * pair of groups (ga < gb) joined by at least one edge the result holds
+ *   weight  = the weights of the joining edges added in product order (row position major, column
+ *             position minor): the reference's float64 running sum, bit for bit,
+ *   edges   = number of joining edges,
+ *   over    = number of edges at which the running sum exceeded `cutoff` (how often karma.py:116-117
+ *             appends the pair),
+ * ordered by (ga, gb) = itertools.combinations order.  Sub-cluster partition: both roles = the node's
+ * sub-cluster.  Two node lists: row role = (0, index in nodes_a), column role = (1, index in nodes_b).
+ * A node must not occur twice in one list.  n_groups > every group id, max_pos >= every position.
+ * kb_links_build synchronises and keeps the result in the context; kb_links_fetch copies it out
+ * (any output pointer may be NULL). */
+KB_API int kb_links_build(kb_ctx* ctx, int64_t n_edges, const int32_t* d_a, const int32_t* d_b, const double* d_weight,
+                   int64_t n_nodes, const int32_t* d_row_group, const int32_t* d_row_pos,
+                   const int32_t* d_col_group, const int32_t* d_col_pos,
+                   int64_t n_groups, int64_t max_pos, double cutoff, int64_t* n_pairs);
+KB_API int kb_links_fetch(kb_ctx* ctx, int32_t* h_group_a, int32_t* h_group_b, double* h_weight, int64_t* h_edges,
+                   int64_t* h_over);
+
 /* Per-stage device times.  With timing enabled every launch of a stage is bracketed
  * by a CUDA-event pair on the context stream (a ring of 128 pairs per stage).
  * kb_stage_ms synchronises, returns the mean duration (ms) and the number of launches
  * recorded since the last read, and resets the stage.
  *  which: 0 count, 1 count-long, 2 compact, 3 normalise, 4 knn-gemm, 5 rerank, 6 exact side path,
- *         7 read-graph build */
+ *         7 read-graph build, 8 group-pair connection weights */
 KB_API int kb_enable_timing(kb_ctx* ctx, int on);
 KB_API int kb_stage_ms(kb_ctx* ctx, int which, float* mean_ms, int* n_launches);
 /* Number of kernels this library launched since the context was created. */

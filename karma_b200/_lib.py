@@ -5,7 +5,7 @@ fails, a KarmaB200Error is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkarma_b200.so")
@@ -16,7 +16,7 @@ KB_MODE_DENSE_4_5 = 2
 KB_KNN_AUTO, KB_KNN_SIMT, KB_KNN_TC = 0, 1, 2
 KB_ENOGPU = -3
 
-STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5, "knn_exact": 6, "readgraph": 7}
+STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5, "knn_exact": 6, "readgraph": 7, "links": 8}
 
 
 def KB_MODE_K(k):
@@ -57,6 +57,8 @@ SIGNATURES = {
     "kb_eq_close": (c_int, [_P]),
     "kb_readgraph_build": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, POINTER(c_int64)]),
     "kb_readgraph_fetch": (c_int, [_P, _P, _P, _P, _P]),
+    "kb_links_build": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_double, POINTER(c_int64)]),
+    "kb_links_fetch": (c_int, [_P, _P, _P, _P, _P, _P]),
     "kb_enable_timing": (c_int, [_P, c_int]),
     "kb_stage_ms": (c_int, [_P, c_int, POINTER(c_float), POINTER(c_int)]),
     "kb_launch_count": (c_int64, [_P]),

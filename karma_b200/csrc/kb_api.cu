@@ -87,7 +87,26 @@ extern "C" int kb_destroy(kb_ctx* c) {
     cudaFree(c->d_k1_scratch);
     kb_free_exotic(c);
     cudaFree(c->d_rg_a); cudaFree(c->d_rg_b); cudaFree(c->d_rg_w); cudaFree(c->d_rg_shared);
+    kb_links_free(c);
+    if (c->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(c->pool); }
     free(c);
+    return KB_OK;
+}
+
+// Temporaries of multi-phase builds come from a per-context stream-ordered pool that never gives memory
+// back to the driver (release threshold = max), so a repeated build allocates nothing.
+int kb_pool_get(kb_ctx* c, cudaMemPool_t* out) {
+    if (!c->pool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = c->device;
+        KB_CUDA(cudaMemPoolCreate(&c->pool, &props));
+        unsigned long long keep = ~0ull;
+        KB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    *out = c->pool;
     return KB_OK;
 }
 

@@ -7,7 +7,7 @@
 #include <cstdarg>
 #include "../../include/karma_b200.h"
 
-#define KB_N_TIMERS 8
+#define KB_N_TIMERS 9
 #define KB_EV_RING 128
 
 struct kb_ctx {
@@ -30,6 +30,11 @@ struct kb_ctx {
     int64_t ex_n_keys, ex_n_entries;
     // read-graph edges of the last kb_readgraph_build (owned)
     int32_t* d_rg_a; int32_t* d_rg_b; double* d_rg_w; uint64_t* d_rg_shared; int64_t rg_edges;
+    // group-pair connection weights of the last kb_links_build: one grow-only scratch block (owned), results point into it
+    void* d_lk_scratch; int64_t lk_scratch_bytes;
+    int32_t* d_lk_a; int32_t* d_lk_b; double* d_lk_w; int64_t* d_lk_edges; int64_t* d_lk_over; int64_t lk_pairs;
+    // stream-ordered pool for the temporaries of the read-graph build (created lazily, keeps its memory)
+    cudaMemPool_t pool;
     // tensor-map encoder (driver entry point, resolved lazily)
     void* encode_tiled;
 };
@@ -74,5 +79,8 @@ int kb_mode_describe(int mode, KbMode* out);
 int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases,
                             const int64_t* d_offsets, int64_t n, uint32_t* d_counts,
                             int64_t ld, uint32_t* d_exotic, uint32_t* d_presence);
+
+void kb_links_free(kb_ctx* c);
+int kb_pool_get(kb_ctx* c, cudaMemPool_t* out);
 
 static inline int64_t kb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

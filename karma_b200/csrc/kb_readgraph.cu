@@ -36,12 +36,17 @@ struct kb_eq {
 
 namespace {
 
+// temporary from the context's stream-ordered pool, returned to it (not to the driver) when it goes out of scope
 struct DevBuf {
+    static thread_local cudaMemPool_t pool;
+    static thread_local cudaStream_t stream;
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, stream); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, stream); }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
+thread_local cudaMemPool_t DevBuf::pool = nullptr;
+thread_local cudaStream_t DevBuf::stream = 0;
 
 __global__ void rg_totals(const int64_t* __restrict__ class_off, const int32_t* __restrict__ ids,
                           const int64_t* __restrict__ counts, int64_t n_classes, unsigned long long* __restrict__ totals) {
@@ -236,6 +241,8 @@ extern "C" int kb_readgraph_build(kb_ctx* ctx, int64_t n_contigs, int64_t n_clas
     KB_CHECK_ARG(n_contigs >= 0 && n_contigs < (1LL << 31) && n_classes >= 0, "sizes");
     KB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    { int rc = kb_pool_get(ctx, &DevBuf::pool); if (rc) return rc; }
+    DevBuf::stream = st;
     rg_free(ctx);
     *n_edges = 0;
     KB_CUDA(cudaMemsetAsync(d_totals, 0, (size_t)n_contigs * 8, st));

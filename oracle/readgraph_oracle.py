@@ -121,9 +121,9 @@ def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_DIR, "read_graph.py"))
 
 
-def reference_build(eq_path, fasta_keys=()):
-    """Run the real ReadGraph.from_equivalence_classes (matplotlib stubbed; `from logs import
-    logger` resolved from the reference directory, karma.log written to a scratch dir)."""
+def load_reference_module():
+    """The real read_graph module (matplotlib stubbed; `from logs import logger` resolved from the
+    reference directory, karma.log written to a scratch dir)."""
     for name in ("matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
@@ -137,7 +137,17 @@ def reference_build(eq_path, fasta_keys=()):
     finally:
         sys.path.remove(REFERENCE_DIR)
         os.chdir(cwd)
-    g = ref_rg.ReadGraph.from_equivalence_classes(eq_path, {k: "" for k in fasta_keys})
+    return ref_rg
+
+
+def reference_graph(eq_path, fasta_keys=()):
+    """The real ReadGraph.from_equivalence_classes result (a networkx graph subclass)."""
+    return load_reference_module().ReadGraph.from_equivalence_classes(eq_path, {k: "" for k in fasta_keys})
+
+
+def reference_build(eq_path, fasta_keys=()):
+    """Run the real ReadGraph.from_equivalence_classes and describe what a consumer can observe."""
+    g = reference_graph(eq_path, fasta_keys)
     nodes = list(g.nodes())
     idx = {k: i for i, k in enumerate(nodes)}
     edges = [(idx[a], idx[b], d["weight"]) for a, b, d in g.edges(data=True)]
