@@ -14,6 +14,16 @@ file:
                  d2_ij = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2, compared by
                  cross-multiplication in Python ints (defines truth under ties).
 * ``check_knn``  the stated-ties parity rule (1e-5 relative on d2).
+* ``knn_umap_small_data``  restatement of umap-learn 0.3.9's neighbour search for fewer than 4096
+                 rows, the only branch of that package that is exact: ``fit`` casts the data to
+                 float32 (check_array), builds ``sklearn.metrics.pairwise_distances(X, metric=
+                 "euclidean")`` and takes, per row, ``argsort(kind="quicksort")[:n_neighbors]``
+                 with the distances read back from the matrix [published algorithm, from memory of
+                 umap/umap_.py 0.3.x: ``UMAP.fit`` small-data branch, ``nearest_neighbors`` with
+                 metric="precomputed", ``fast_knn_indices``].  scikit-learn IS in this image, so this
+                 leg runs the third-party function the reference would call; tests/golden/
+                 knn_umap_small_golden.npz holds its output (oracle/make_golden_knn.py).  It is a
+                 weaker pin than a reference-owned vector: stated, not hidden.
 """
 import numpy as np
 
@@ -30,11 +40,13 @@ def d2_fp64(profile, rows=None):
     return out
 
 
-def knn_fp64(profile, k, rows=None):
-    """(idx int64 (R,k), d2 float64 (R,k)): self first, then (distance, index)."""
+def knn_fp64(profile, k, rows=None, d2=None):
+    """(idx int64 (R,k), d2 float64 (R,k)): self first, then (distance, index).
+    ``d2``: the rows' distances if the caller already has them (d2_fp64(profile, rows))."""
     p = np.asarray(profile, dtype=np.float64)
     ridx = np.arange(p.shape[0]) if rows is None else np.asarray(rows)
-    d2 = d2_fp64(p, ridx)
+    if d2 is None:
+        d2 = d2_fp64(p, ridx)
     n = p.shape[0]
     out_i = np.empty((len(ridx), k), dtype=np.int64)
     out_d = np.empty((len(ridx), k), dtype=np.float64)
@@ -67,6 +79,23 @@ def knn_exact(counts, key_len, k, rows=None):
         out_i.append([j for _, j in keyed[:k]])
         out_d.append([float(d) for d, _ in keyed[:k]])
     return np.array(out_i, dtype=np.int64), np.array(out_d, dtype=np.float64)
+
+
+def knn_umap_small_data(profile, k):
+    """(idx int64 (N,k), dist float32 (N,k)) as umap-learn 0.3.9 computes them for N < 4096."""
+    from sklearn.metrics import pairwise_distances
+    x = np.ascontiguousarray(np.asarray(profile), dtype=np.float32)
+    dmat = pairwise_distances(x, metric="euclidean")
+    idx = np.argsort(dmat, axis=1, kind="quicksort")[:, :k]
+    return idx.astype(np.int64), dmat[np.arange(dmat.shape[0])[:, None], idx].astype(np.float32)
+
+
+def agreement(idx_a, idx_b):
+    """Fraction of rows with the same neighbour SET, and with the same neighbour ORDER."""
+    a, b = np.asarray(idx_a), np.asarray(idx_b)
+    same_set = np.array([set(x.tolist()) == set(y.tolist()) for x, y in zip(a, b)])
+    same_order = (a == b).all(axis=1)
+    return float(same_set.mean()), float(same_order.mean())
 
 
 def check_knn(idx, dist, truth_d2, rows=None, rtol=1e-5, sqrt_dist=True):
