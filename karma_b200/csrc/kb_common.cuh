@@ -81,6 +81,9 @@ int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases
                             int64_t ld, uint32_t* d_exotic, uint32_t* d_presence);
 
 void kb_links_free(kb_ctx* c);
+// host-side file input shared by the FASTA and eq_classes parsers (kb_fasta.cu)
+int64_t kb_host_threads();
+int kb_host_read_file(const char* path, uint8_t** img, int64_t* size);
 int kb_pool_get(kb_ctx* c, cudaMemPool_t* out);
 
 static inline int64_t kb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 struct kb_eq {
@@ -151,58 +152,132 @@ bool parse_int(const uint8_t* p, const uint8_t* e, int64_t* out) {
 // ---------------------------------------------------------------------------------------
 // host: eq_classes.txt parser (read_graph.py:75-82)
 // ---------------------------------------------------------------------------------------
+namespace {
+
+// One chunk of class lines, "first<TAB>id...<TAB>count" each (at least two fields).
+struct EqChunk {
+    const uint8_t* beg = nullptr; const uint8_t* end = nullptr;
+    std::vector<int32_t> ids;
+    std::vector<int32_t> sizes;            // ids per class
+    std::vector<int64_t> counts;
+    std::vector<uint8_t> skip;
+    const char* error = nullptr;           // first malformed line of the chunk
+};
+
+void parse_eq_chunk(EqChunk& c, int64_t n_contigs) {
+    const uint8_t* p = c.beg;
+    const size_t guess = (size_t)(c.end - c.beg) / 24 + 16;   // ~30 bytes per class in salmon's files
+    c.sizes.reserve(guess); c.counts.reserve(guess); c.skip.reserve(guess); c.ids.reserve(guess * 4);
+    while (p < c.end) {
+        const uint8_t* nl = static_cast<const uint8_t*>(memchr(p, '\n', (size_t)(c.end - p)));
+        const uint8_t* e = nl ? nl : c.end;
+        // first token: only "is it exactly 1" matters (read_graph.py:102)
+        const uint8_t* t = static_cast<const uint8_t*>(memchr(p, '\t', (size_t)(e - p)));
+        if (!t) { c.error = "malformed equivalence class line"; return; }
+        const uint8_t skip = (t - p == 1 && *p == '1') ? 1 : 0;
+        // the remaining tokens are integers; the last one is the read count, the others contig ids
+        int32_t n_ids = 0;
+        bool have = false;
+        int64_t pending = 0;
+        const uint8_t* s = t + 1;
+        for (;;) {
+            const uint8_t* t2 = static_cast<const uint8_t*>(memchr(s, '\t', (size_t)(e - s)));
+            const uint8_t* te = t2 ? t2 : e;
+            if (have) {                                        // the previous token was not the last: a contig id
+                if (pending < 0 || pending >= n_contigs) { c.error = "contig id out of range"; return; }
+                c.ids.push_back((int32_t)pending);
+                ++n_ids;
+            }
+            if (!parse_int(s, te, &pending)) { c.error = t2 ? "contig id out of range" : "class count is not an integer"; return; }
+            have = true;
+            if (!t2) break;
+            s = t2 + 1;
+        }
+        c.sizes.push_back(n_ids);
+        c.counts.push_back(pending);
+        c.skip.push_back(skip);
+        p = nl ? nl + 1 : c.end;
+    }
+}
+
+}  // namespace
+
 extern "C" int kb_eq_open(const char* path, kb_eq** out, int64_t* n_contigs, int64_t* n_classes, int64_t* n_ids,
                           int64_t* name_bytes) {
     KB_CHECK_ARG(path && out, "null pointer");
     *out = nullptr;
-    FILE* fp = fopen(path, "rb");
-    if (!fp) { kb_set_error("cannot open %s", path); return KB_EINVAL; }
-    fseek(fp, 0, SEEK_END);
-    const long sz = ftell(fp);
-    fseek(fp, 0, SEEK_SET);
-    std::vector<uint8_t> img(sz > 0 ? (size_t)sz : 0);
-    if (sz > 0 && fread(img.data(), 1, (size_t)sz, fp) != (size_t)sz) { fclose(fp); kb_set_error("short read on %s", path); return KB_EINVAL; }
-    fclose(fp);
+    uint8_t* img = nullptr;
+    int64_t sz = 0;
+    { const int rc = kb_host_read_file(path, &img, &sz); if (rc) return rc; }
+    struct Guard { uint8_t* p; ~Guard() { free(p); } } guard{img};
     kb_eq* q = new kb_eq();
-    const uint8_t* p = img.data();
-    const uint8_t* end = p + img.size();
+    const uint8_t* p = img;
+    const uint8_t* end = img + sz;
     auto next_line = [&](const uint8_t*& b, const uint8_t*& e) -> bool {
         if (p >= end) return false;
         b = p;
-        while (p < end && *p != '\n') ++p;
-        e = p;
-        if (p < end) ++p;
+        const uint8_t* nl = static_cast<const uint8_t*>(memchr(p, '\n', (size_t)(end - p)));
+        e = nl ? nl : end;
+        p = nl ? nl + 1 : end;
         return true;
     };
     const uint8_t *b, *e;
     int64_t n = 0;
     if (!next_line(b, e) || !parse_int(b, e, &n) || n < 0) { delete q; kb_set_error("%s: first line is not the contig count", path); return KB_EINVAL; }
     next_line(b, e);                                            // number of classes: ignored like the reference does
+    q->name_off.reserve((size_t)n + 1);
     q->name_off.push_back(0);
     for (int64_t i = 0; i < n; ++i) {
         if (!next_line(b, e)) { b = e = end; }                  // readline() past EOF gives ""
         q->names.insert(q->names.end(), b, e);
         q->name_off.push_back((int64_t)q->names.size());
     }
-    q->class_off.push_back(0);
-    while (next_line(b, e)) {
-        // "first<TAB>id...<TAB>count": at least two tab-separated fields
-        std::vector<std::pair<const uint8_t*, const uint8_t*>> f;
-        const uint8_t* s = b;
-        for (const uint8_t* t = b; ; ++t) {
-            if (t == e || *t == '\t') { f.emplace_back(s, t); s = t + 1; if (t == e) break; }
+    // the class lines: chunks of >= 1 MB cut after a '\n', one thread each
+    int64_t want = kb_host_threads();
+    const int64_t body = (int64_t)(end - p);
+    const int64_t min_chunk = getenv("KB_EQ_MIN_CHUNK") ? atoll(getenv("KB_EQ_MIN_CHUNK")) : (1LL << 20);
+    if (want > body / (min_chunk > 0 ? min_chunk : 1) + 1) want = body / (min_chunk > 0 ? min_chunk : 1) + 1;
+    std::vector<EqChunk> chunks;
+    const uint8_t* prev = p;
+    for (int64_t t = 1; t <= want; ++t) {
+        const uint8_t* cut = t == want ? end : p + body * t / want;
+        while (cut < end && cut > p && cut[-1] != '\n') ++cut;
+        if (cut > prev) { EqChunk c; c.beg = prev; c.end = cut; chunks.push_back(std::move(c)); prev = cut; }
+    }
+    if (chunks.size() <= 1) { for (auto& c : chunks) parse_eq_chunk(c, n); }
+    else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < chunks.size(); ++i) th.emplace_back([&, i] { parse_eq_chunk(chunks[i], n); });
+        for (auto& t : th) t.join();
+    }
+    size_t tot_classes = 0, tot_ids = 0;
+    for (auto& c : chunks) {
+        if (c.error) { delete q; kb_set_error("%s: %s", path, c.error); return KB_EINVAL; }
+        tot_classes += c.counts.size(); tot_ids += c.ids.size();
+    }
+    q->class_off.resize(tot_classes + 1);
+    q->ids.resize(tot_ids); q->counts.resize(tot_classes); q->skip.resize(tot_classes);
+    {
+        std::vector<size_t> c0(chunks.size()), i0(chunks.size());
+        size_t cc = 0, ii = 0;
+        for (size_t i = 0; i < chunks.size(); ++i) { c0[i] = cc; i0[i] = ii; cc += chunks[i].counts.size(); ii += chunks[i].ids.size(); }
+        auto place = [&](size_t i) {
+            EqChunk& c = chunks[i];
+            if (!c.ids.empty()) memcpy(q->ids.data() + i0[i], c.ids.data(), c.ids.size() * 4);
+            if (!c.counts.empty()) {
+                memcpy(q->counts.data() + c0[i], c.counts.data(), c.counts.size() * 8);
+                memcpy(q->skip.data() + c0[i], c.skip.data(), c.skip.size());
+            }
+            int64_t at = (int64_t)i0[i];
+            for (size_t k = 0; k < c.sizes.size(); ++k) { q->class_off[c0[i] + k] = at; at += c.sizes[k]; }
+        };
+        if (chunks.size() <= 1) { for (size_t i = 0; i < chunks.size(); ++i) place(i); }
+        else {
+            std::vector<std::thread> th;
+            for (size_t i = 0; i < chunks.size(); ++i) th.emplace_back(place, i);
+            for (auto& t : th) t.join();
         }
-        if (f.size() < 2) { delete q; kb_set_error("%s: malformed equivalence class line", path); return KB_EINVAL; }
-        int64_t cnt = 0;
-        if (!parse_int(f.back().first, f.back().second, &cnt)) { delete q; kb_set_error("%s: class count is not an integer", path); return KB_EINVAL; }
-        for (size_t k = 1; k + 1 < f.size(); ++k) {
-            int64_t id = 0;
-            if (!parse_int(f[k].first, f[k].second, &id) || id < 0 || id >= n) { delete q; kb_set_error("%s: contig id out of range", path); return KB_EINVAL; }
-            q->ids.push_back((int32_t)id);
-        }
-        q->class_off.push_back((int64_t)q->ids.size());
-        q->counts.push_back(cnt);
-        q->skip.push_back((f[0].second - f[0].first == 1 && *f[0].first == '1') ? 1 : 0);
+        q->class_off[tot_classes] = (int64_t)tot_ids;
     }
     if (n_contigs) *n_contigs = n;
     if (n_classes) *n_classes = (int64_t)q->counts.size();

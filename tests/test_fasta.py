@@ -42,8 +42,11 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("threads", [1, 5])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_matches_reference_reader(tmp_path, name):
+def test_matches_reference_reader(tmp_path, monkeypatch, name, threads):
+    monkeypatch.setenv("KB_HOST_THREADS", str(threads))      # 5 threads + 1-byte chunks: cuts inside records
+    monkeypatch.setenv("KB_FASTA_MIN_CHUNK", "1")
     path = tmp_path / (name + ".fa")
     with open(path, "wb") as f:
         f.write(CASES[name].encode("ascii"))
@@ -59,7 +62,7 @@ def test_matches_reference_reader(tmp_path, name):
         assert key_len.tolist() == [len(k) for k in want]
 
 
-def test_large_random_fasta_and_kmer_pack(tmp_path):
+def test_large_random_fasta_and_kmer_pack(tmp_path, monkeypatch):
     from karma_b200 import synth
     from karma_b200.kmer import KmerClustering
     asm = synth.s1_families(300, seed=2)
@@ -72,6 +75,9 @@ def test_large_random_fasta_and_kmer_pack(tmp_path):
                 f.write(s[i:i + 60] + "\n")
     got = fasta.read_fasta_file(path)
     assert list(got.items()) == list(d.items())
+    monkeypatch.setenv("KB_FASTA_MIN_CHUNK", "20000")         # ~17 chunks over the 340 KB file
+    monkeypatch.setenv("KB_HOST_THREADS", "32")
+    assert list(fasta.read_fasta_file(path).items()) == list(d.items())
     bases, offsets, key_len = KmerClustering(got, "/tmp", "5p6", 1)._pack()
     assert np.array_equal(bases, asm.bases) and np.array_equal(offsets, asm.offsets) and np.array_equal(key_len, asm.key_len)
     got[">extra"] = "ACGT"                      # a modified mapping falls back to the generic packer

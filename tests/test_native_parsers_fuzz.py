@@ -15,9 +15,20 @@ line_endings = st.sampled_from(["\n", "\r\n", "\r"])
 lines = st.lists(st.tuples(st.text(alphabet=ALPHABET, min_size=0, max_size=40), line_endings), min_size=0, max_size=25)
 
 
+@pytest.fixture(params=["one_chunk", "tiny_chunks"])
+def chunking(request, monkeypatch):
+    """The packer cuts the file image into per-thread chunks of >= 4 MB; `tiny_chunks` forces a cut at
+    (almost) every line so that records, sequence lines and "\r\n" pairs straddle chunk borders."""
+    if request.param == "tiny_chunks":
+        monkeypatch.setenv("KB_FASTA_MIN_CHUNK", "1")
+        monkeypatch.setenv("KB_EQ_MIN_CHUNK", "1")
+        monkeypatch.setenv("KB_HOST_THREADS", "13")
+    return request.param
+
+
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(body=lines, trailing=st.booleans())
-def test_fasta_packer_equals_reference_reader(tmp_path, body, trailing):
+def test_fasta_packer_equals_reference_reader(tmp_path, chunking, body, trailing):
     text = "".join(l + e for l, e in body)
     if not trailing and body:
         text = text[:-len(body[-1][1])]
@@ -41,7 +52,7 @@ classes_st = st.lists(st.tuples(st.sampled_from(["1", "2", "3", "7"]),
 
 @settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(classes=classes_st)
-def test_eq_parser_equals_python_parser(tmp_path, classes):
+def test_eq_parser_equals_python_parser(tmp_path, chunking, classes):
     from karma_b200 import read_graph as rg
     names = ["contig_%d x" % i for i in range(12)]
     path = os.path.join(str(tmp_path), "eq.txt")

@@ -57,12 +57,29 @@ def test_native_parser_matches_python_parser(tmp_path, rg_golden):
         assert p["skip"].tolist() == [1 if f == "1" else 0 for f, _, _ in classes]
 
 
-def test_native_parser_rejects_bad_input(tmp_path):
+@pytest.mark.parametrize("threads", [1, 6])
+@pytest.mark.parametrize("body,why", [
+    ("2\t0\t5\t3\n", "contig id 5 out of range"),
+    ("2\t0\t1\t3\n2\t0\t-1\t3\n", "negative contig id"),
+    ("2\t0\t1\tx\n", "count is not an integer"),
+    ("2\t0\t1\t\n", "empty count"),
+    ("2\t0\t1\t4\n\n2\t0\t1\t4\n", "blank line (the reference fails to unpack it)"),
+    ("2 0 1 4\n", "no tab at all"),
+    ("2\t0\t1 \t4\n", "id with a trailing blank"),
+])
+def test_native_parser_rejects_bad_input(tmp_path, monkeypatch, body, why, threads):
     from karma_b200 import _lib, read_graph as rg
+    monkeypatch.setenv("KB_HOST_THREADS", str(threads))
+    monkeypatch.setenv("KB_EQ_MIN_CHUNK", "1")
     p = tmp_path / "bad.txt"
-    p.write_text("2\n1\na\nb\n2\t0\t5\t3\n")            # contig id 5 out of range
+    p.write_text("2\n1\na\nb\n2\t0\t1\t7\n" + body + "1\t1\t2\n")
     with pytest.raises(_lib.KarmaB200Error):
         rg.parse(str(p))
+    good = tmp_path / "good.txt"
+    good.write_text("2\n1\na\nb\n2\t0\t1\t7\n1\t1\t2")         # last line without a newline
+    got = rg.parse(str(good))
+    assert got["names"] == ["a", "b"] and got["ids"].tolist() == [0, 1, 1] and got["counts"].tolist() == [7, 2]
+    assert got["class_off"].tolist() == [0, 2, 3] and got["skip"].tolist() == [0, 1]
 
 
 @pytest.mark.gpu
