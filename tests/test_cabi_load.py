@@ -86,3 +86,28 @@ def test_product_never_imports_oracle():
     for path in glob.glob(os.path.join(ROOT, "karma_b200", "**", "*.py"), recursive=True):
         src = open(path).read()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), path
+
+
+def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
+    """include/karma_b200.h is consumed by a C99 compiler (no C++, no torch types) and a plain-C host
+    program links against the library; without a GPU it stops at kb_create with the no-fallback error."""
+    import shutil
+    import subprocess
+    from karma_b200 import _lib
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gcc or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA headers are not available")
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lkarma_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+           "-Wl,-rpath," + libdir, "-o", exe]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    assert built.returncode == 0, built.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "c_abi_demo OK" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode != 0 and "no CPU fallback" in run.stderr, run.stdout + run.stderr
