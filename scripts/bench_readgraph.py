@@ -12,7 +12,6 @@ import sys
 import tempfile
 import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

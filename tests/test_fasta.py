@@ -1,6 +1,4 @@
 """Native FASTA packer == read_fasta_file of the reference (karma.py:40-61), host only."""
-import io
-import os
 from collections import OrderedDict
 
 import numpy as np

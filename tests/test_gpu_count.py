@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from karma_b200 import _lib, synth
+from karma_b200 import synth
 from karma_b200.engine import mode_of
 from oracle import kmer_oracle as ko
 

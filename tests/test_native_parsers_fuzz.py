@@ -2,7 +2,6 @@
 eq_classes file holds, the C packers must agree with the reference's Python readers."""
 import os
 
-import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
 

@@ -2,7 +2,6 @@
 /root/reference does not travel to the GPU box, where these tests skip)."""
 import random
 
-import numpy as np
 import pytest
 
 from oracle import kmer_oracle as ko

@@ -3,7 +3,6 @@ native eq_classes parser, and (GPU) the device build against the oracle."""
 import json
 import os
 
-import numpy as np
 import pytest
 
 from oracle import readgraph_oracle as ro
