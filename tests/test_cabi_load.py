@@ -111,3 +111,25 @@ def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
         assert run.returncode == 0 and "c_abi_demo OK" in run.stdout, run.stdout + run.stderr
     else:
         assert run.returncode != 0 and "no CPU fallback" in run.stderr, run.stdout + run.stderr
+
+
+def test_knn_plan_workspace_bounds(lib, monkeypatch):
+    """kb_knn_workspace_bytes (host only) over the shapes of BASELINE.json and the shard shapes of 2-8 GPUs:
+    the plan never asks for more candidate slots than K5 can merge (512 per row) and always covers the
+    per-key metadata, for every cluster variant."""
+    from karma_b200 import _lib
+    shapes = [(1000, 1000), (50000, 50000), (6250, 50000), (62500, 500000), (125000, 1000000), (250000, 2000000), (130, 130), (513, 513)]
+    for cluster in (None, "1", "2", "4"):
+        if cluster is None:
+            monkeypatch.delenv("KB_KNN_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("KB_KNN_CLUSTER", cluster)
+        for nq, nk in shapes:
+            for k in (2, 10, 15, 24):
+                kp = 8 if k <= 2 else 16 if k <= 10 else 24 if k <= 18 else 32
+                for impl in (_lib.KB_KNN_SIMT, _lib.KB_KNN_TC):
+                    b = lib.kb_knn_workspace_bytes(nq, nk, k, impl, 0)
+                    lo = nk * 8 + nq * kp * 8 + nq * 4                       # colmeta + one split of candidates + row bounds
+                    hi = (nk + 256) * 8 + nq * 512 * 8 + nq * 4 + 8 * 256    # at most 512 candidates per row
+                    assert lo <= b <= hi, (cluster, nq, nk, k, impl, b, lo, hi)
+                    assert lib.kb_knn_workspace_bytes(nq, nk, k, impl, 7) > b    # flagged rows add the fp64 side lists
