@@ -37,7 +37,7 @@ int main(void) {
     CUDA(cudaMemset(d_presence, 0, (size_t)(D + 1) * 4));
 
     CHECK(kb_count(ctx, KB_MODE_5P6, d_bases, d_off, N, d_counts, D, d_exotic, d_presence));          /* kmer.py:56-92 */
-    CHECK(kb_normalise(ctx, d_counts, D, D, d_len, N, d_profile, D, NULL, 0, NULL));                  /* count / len(key) */
+    CHECK(kb_normalise(ctx, d_counts, D, D, d_len, N, N, d_profile, D, NULL, 0, NULL, NULL, NULL));                  /* count / len(key) */
     double* profile = (double*)malloc((size_t)N * D * 8);
     CUDA(cudaMemcpy(profile, d_profile, (size_t)N * D * 8, cudaMemcpyDeviceToHost));
     /* column 0 = "AAAAA", column 1 = "AAAAAA" (sorted order of kmer.py:172): 6/11 and 5/11 for >contig_two */

@@ -34,14 +34,19 @@ extern "C" {
 
 typedef struct kb_ctx kb_ctx;
 
-/* Per-contig metadata of the kNN stage, produced by kb_normalise, consumed by kb_knn.
- * One 16-byte record per row, so that a row shard travels in ONE all-gather. */
+/* Per-contig record of the kNN stage, produced by kb_normalise, consumed by kb_knn.
+ * One 32-byte record per row, so that a row shard travels in ONE exchange step. */
 typedef struct kb_rowmeta {
     double  sqnorm;   /* sum_c count^2 (exact integer)                                   */
     int32_t key_len;  /* len(header key incl. '>'), what kmer.py:213 divides by          */
     int32_t flags;    /* bit0: some count > 2048 (fp16 operand saturated)
                          bit1: sqnorm >= 2^24 (fp32 Gram not exact)
-                         bit2: all-zero row (kmer.py:250-258 exits)                      */
+                         bit2: all-zero row (kmer.py:250-258 exits)
+                         bit3: padding row of a multi-rank gather (never a neighbour)     */
+    float   cm_x;     /* -2/key_len            } score of this row as a KEY in K4:        */
+    float   cm_y;     /* sqnorm/key_len^2      } fma(g_ij, cm_x, l_i*cm_y) = l_i*d2_ij - n_i/l_i;
+                         +inf when flags & 11: the tensor path never proposes the row      */
+    int32_t reserved[2];
 } kb_rowmeta;
 
 /* error codes */
@@ -68,6 +73,9 @@ typedef struct kb_rowmeta {
 #define KB_MODE_DENSE_5_6  1
 #define KB_MODE_DENSE_4_5  2
 #define KB_MODE_K(k)       (16 + (k))
+/* OR-ed into kb_count's mode: d_presence then receives only [D] ("a non-ACGT byte was seen");
+ * the per-column words are left alone (kb_normalise can derive them from the rows it reads). */
+#define KB_COUNT_NO_COLUMNS 0x100
 
 /* kNN implementations */
 #define KB_KNN_AUTO   0
@@ -153,15 +161,21 @@ KB_API int kb_compact(kb_ctx* ctx, const uint32_t* d_in, int64_t ld_in, int32_t 
  * key_len[i] = len(header key incl. '>') (kmer.py:213).  Also emits what the
  * kNN consumes.  Any output may be NULL.
  *  d_profile  double[n*ld_profile]
- *  d_operand  fp16 [n*ld_operand]   raw counts as fp16 (exact <= 2048), columns
+ *  d_operand  fp16 [n_alloc*ld_operand]  raw counts as fp16 (exact <= 2048), columns
  *                                   [d_cols, ld_operand) zero-filled;
  *                                   ld_operand % 64 == 0
- *  d_rowmeta  kb_rowmeta[n]         squared norm, key length and flags per row */
+ *  d_rowmeta  kb_rowmeta[n_alloc]   squared norm, key length, flags and K4 constants per row
+ *  n_alloc    >= n: rows [n, n_alloc) of operand/rowmeta are written as gather padding
+ *             (zero counts, flags 1|2|8) so that equal-size shards can be exchanged
+ *  d_presence uint32[d_cols+1] (accumulates; zero it first): [c] != 0 iff column c is
+ *             non-zero in some row -- OR bit1 of [d_cols] is set, which proves that EVERY
+ *             column is present (one CTA saw them all and skipped the per-column stores)
+ *  d_flags_or uint32[1] (accumulates): OR of kb_rowmeta.flags over rows [0,n) */
 KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32_t d_cols,
-                 const int32_t* d_key_len, int64_t n,
+                 const int32_t* d_key_len, int64_t n, int64_t n_alloc,
                  double* d_profile, int64_t ld_profile,
                  void* d_operand, int64_t ld_operand,
-                 kb_rowmeta* d_rowmeta);
+                 kb_rowmeta* d_rowmeta, uint32_t* d_presence, uint32_t* d_flags_or);
 
 /* OR of kb_rowmeta.flags over rows [0,n) (padding rows, bit3, excluded) into *d_out:
  * lets the host validate a whole pass by reading one word. */
@@ -170,23 +184,46 @@ KB_API int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t
 /* ---- K4 + K5: exact kNN ----------------------------------------------------
  * Replaces the neighbour search inside umap.UMAP(...).fit_transform at
  * kmer.py:285-290 (euclidean metric over the profile rows, the point itself
- * included as neighbour 0).  Queries are a row range of the (possibly
- * all-gathered) key set: query q is key row q_row0 + q.
+ * included as neighbour 0; any n_neighbors the reference's CLI accepts,
+ * cmd_parser.py:101-107).  Queries are a row range of the (possibly gathered)
+ * key set: query q is key row q_row0 + q.
  *
  * Candidate search: integer Gram matrix of the raw counts on the tensor cores
  * (fp16 in, fp32 accumulate: exact while counts <= 2048 and sqnorm < 2^24),
- * distances by norm expansion, per-row running top-k' in the epilogue.
- * Then K5 reranks the k' candidates exactly:
+ * distances by norm expansion, per-row running top-k' in the epilogue
+ * (k' = 8..64 for k <= 60).  Then K5 reranks the k' candidates exactly:
  *   d2 = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2     (fp64)
- * and orders by (self first, d2, index).  d_dist receives sqrt(d2) as float
- * (UMAP's knn_dists), d_d2 (nullable) the fp64 squared distances.
+ * orders by (self first, d2, index) and CERTIFIES every row: with s = l_i*d2 - n_i/l_i the
+ * exact score of its k-th neighbour, B the k'-th best fp32 score (every key that is not a
+ * candidate scored >= B) and E = 2^-22*(Y^2 + 2cY), c^2 = n_i/l_i, Y = c + sqrt(c^2 + s), a bound
+ * on the fp32 evaluation error of any key that could still beat s, the row is final iff
+ * s + 2E < B.  Rows that fail (more than k'-k near-ties: long contigs, mass duplicates) and
+ * every row when k > 60 are listed in the workspace and redone by kb_knn_fixup with exact
+ * distances to ALL keys.
+ * d_dist receives sqrt(d2) as float (UMAP's knn_dists), d_d2 (nullable) the fp64 squared
+ * distances.
  * Exact side path (K4x): rows whose flags bit0/bit1 are set cannot be scored exactly by
  * the tensor path; they are masked there and handled in fp64 from their true counts:
  *  d_flag_rows   int32[n_flag]  ascending key-row indices of ALL flagged rows
  *  d_flag_counts uint32[n_flag*ld_flag_counts]  their count rows (flag_cols columns)
- * (both NULL / 0 when no row is flagged).  Padding rows of a multi-rank gather carry
- * flags = 3|8 and are never candidates.                                         */
-KB_API int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl, int64_t n_flag);
+ * (both NULL / 0 when no row is flagged).
+ * Multi-GPU (peer-memory exchange, see kb_xchg_*): d_arrive/d_epoch (nullable) make the TMA
+ * producer wait until arrive[r] >= *epoch before it touches a key row of source rank
+ * r = row / rows_per_src; peer_idx/peer_dist (n_peers device pointers, nullable) are the
+ * peers' gathered result arrays: K5 stores row q_row0+q there as well (stores over NVLink).
+ * kb_knn only enqueues.  kb_knn_fixup synchronises the stream, returns the number of rows it
+ * had to redo (0 in the common case: then it is a read of one word) or a negative error. */
+/* ctx may be NULL (then a 148-SM B200 is assumed: the number of candidate lists depends on the SM count) */
+KB_API int64_t kb_knn_workspace_bytes(kb_ctx* ctx, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k, int impl, int64_t n_flag);
+typedef struct kb_knn_xchg {
+    const uint32_t* d_arrive;     /* uint32[world]: arrive[r] = epoch of the last shard pushed by rank r */
+    const uint32_t* d_epoch;      /* uint32[1]: epoch of the current pass                                   */
+    int64_t rows_per_src;         /* rows of the gathered key set per source rank                           */
+    int32_t n_peers;              /* entries of peer_idx / peer_dist (0: none)                              */
+    int32_t self_rank;            /* this rank: its own rows are always there                               */
+    int32_t* const* d_peer_idx;   /* device array of n_peers pointers: peers' all_idx [world*rows_per_src, k] */
+    float* const* d_peer_dist;    /* device array of n_peers pointers: peers' all_dist                      */
+} kb_knn_xchg;
 KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
            const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
            const kb_rowmeta* d_rowmeta,
@@ -194,7 +231,55 @@ KB_API int kb_knn(kb_ctx* ctx, int impl, int32_t k,
            const int32_t* d_flag_rows, const uint32_t* d_flag_counts, int64_t ld_flag_counts,
            int32_t flag_cols, int64_t n_flag,
            int32_t* d_idx, float* d_dist, double* d_d2,
+           void* d_workspace, int64_t workspace_bytes, const kb_knn_xchg* xchg);
+KB_API int64_t kb_knn_fixup(kb_ctx* ctx, int impl, int32_t k,
+           const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
+           const kb_rowmeta* d_rowmeta,
+           int64_t nk, int64_t q_row0, int64_t nq,
+           const int32_t* d_flag_rows, const uint32_t* d_flag_counts, int64_t ld_flag_counts,
+           int32_t flag_cols, int64_t n_flag,
+           int32_t* d_idx, float* d_dist, double* d_d2,
            void* d_workspace, int64_t workspace_bytes);
+/* Number of uncertified rows recorded by the last kb_knn in this workspace: a device word the
+ * caller may copy back with its other validation words instead of calling kb_knn_fixup. */
+KB_API int kb_knn_uncertified_ptr(kb_ctx* ctx, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k, int impl, int64_t n_flag,
+                           void* d_workspace, const uint32_t** d_count);
+/* Host-only views of the tensor kernel's work schedule (tests, diagnostics): kb_knn_plan_info fills
+ * out[0..7] = candidate width k', lists per row, key bands, schedule kind, workers (CTA clusters), pieces,
+ * 1000 x tile visits of the busiest worker, 1000 x the ideal; kb_knn_plan_table the table itself:
+ * pieces int32[pieces*8] = {group, slot, t_lo, cnt, shift, i_lo, i_cnt, 0}, piece_start int32[workers+1],
+ * slot_count int32[groups]. */
+KB_API int kb_knn_plan_info(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k, int64_t* out);
+KB_API int kb_knn_plan_table(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k,
+                      int32_t* pieces, int32_t* piece_start, int32_t* slot_count);
+
+/* ---- peer-memory exchange of the kNN stage (GPUs of one node; NVLink / NVSwitch) ----------------
+ * the one exchange step of the path.  Every rank owns an "arena" (device memory, same layout
+ * on every rank, mapped by its peers through CUDA IPC).  The first 1 KB is the control block (epoch and
+ * arrival / done / results flags); the caller lays out the gathered arrays behind it.
+ *   kb_xchg_create   allocates the arena and returns the 64-byte IPC handle to hand to the peers
+ *   kb_xchg_attach   maps the peers' arenas (handles: world x 64 bytes, indexed by rank)
+ *   kb_xchg_peer_ptr base address of a peer's arena in THIS process (peer == rank: the local arena)
+ * A pass (all calls only enqueue; the whole pass may be captured in a CUDA graph):
+ *   kb_xchg_begin    on the context stream, first thing: epoch += 1, tell the peers that this rank no longer
+ *                    reads what they pushed for the previous pass
+ *   kb_xchg_push     on `stream` (a side stream ordered after K3): wait until every peer is done with the
+ *                    previous pass, copy this rank's shard of every region -- bytes [off + rank*shard_bytes,
+ *                    +shard_bytes) -- into every peer's arena (copy engines), then arrive[rank] = epoch there
+ *   kb_knn(..xchg..) sweeps the local shard first and waits for arrive[r] before the first key row of rank r
+ *   kb_xchg_finish   on the context stream after K5: copy this rank's record (rec_words u32 at
+ *                    rec_off + rank*rec_words*4) to every peer, raise the results flag everywhere and wait
+ *                    until every peer's results and record have landed here
+ * All waits are bounded (a dead peer traps the kernel after ~10 s instead of hanging the GPU). */
+typedef struct kb_xchg kb_xchg;
+KB_API int kb_xchg_create(kb_ctx* ctx, int world, int rank, int64_t bytes, kb_xchg** out, void** d_local, uint8_t* handle64);
+KB_API int kb_xchg_attach(kb_xchg* x, const uint8_t* handles);
+KB_API int kb_xchg_peer_ptr(kb_xchg* x, int peer, void** d_ptr);
+KB_API int kb_xchg_flags(kb_xchg* x, const uint32_t** d_arrive, const uint32_t** d_epoch);
+KB_API int kb_xchg_destroy(kb_xchg* x);
+KB_API int kb_xchg_begin(kb_xchg* x);
+KB_API int kb_xchg_push(kb_xchg* x, void* stream, int n_regions, const int64_t* region_off, const int64_t* shard_bytes);
+KB_API int kb_xchg_finish(kb_xchg* x, int64_t rec_off, int32_t rec_words);
 
 /* ---- FASTA reader / packer (host only) --------------------------------------------
  * Replaces read_fasta_file (karma.py:40-61) and the dict -> buffer marshalling: same

@@ -15,6 +15,7 @@ KB_MODE_DENSE_5_6 = 1
 KB_MODE_DENSE_4_5 = 2
 KB_KNN_AUTO, KB_KNN_SIMT, KB_KNN_TC = 0, 1, 2
 KB_ENOGPU = -3
+KB_COUNT_NO_COLUMNS = 0x100
 
 STAGES = {"count": 0, "count_long": 1, "compact": 2, "normalise": 3, "knn_gemm": 4, "rerank": 5, "knn_exact": 6, "readgraph": 7, "links": 8}
 
@@ -44,11 +45,24 @@ SIGNATURES = {
     "kb_exotic_fetch": (c_int, [_P, _P, _P, _P, _P]),
     "kb_exotic_scatter": (c_int, [_P, _P, _P, c_int64]),
     "kb_compact": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32]),
-    "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P]),
     "kb_rowmeta_flags_or": (c_int, [_P, _P, c_int64, _P]),
-    "kb_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int32, c_int, c_int64]),
+    "kb_knn_workspace_bytes": (c_int64, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int, c_int64]),
     "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int64,
-                       _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64]),
+                       _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64, _P]),
+    "kb_knn_fixup": (c_int64, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int64,
+                               _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P, c_int64]),
+    "kb_knn_uncertified_ptr": (c_int, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int, c_int64, _P, POINTER(c_void_p)]),
+    "kb_knn_plan_info": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int32, c_int32, POINTER(c_int64)]),
+    "kb_knn_plan_table": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P, _P]),
+    "kb_xchg_create": (c_int, [_P, c_int, c_int, c_int64, POINTER(c_void_p), POINTER(c_void_p), _P]),
+    "kb_xchg_attach": (c_int, [_P, _P]),
+    "kb_xchg_peer_ptr": (c_int, [_P, c_int, POINTER(c_void_p)]),
+    "kb_xchg_flags": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p)]),
+    "kb_xchg_destroy": (c_int, [_P]),
+    "kb_xchg_begin": (c_int, [_P]),
+    "kb_xchg_push": (c_int, [_P, _P, c_int, _P, _P]),
+    "kb_xchg_finish": (c_int, [_P, c_int64, c_int32]),
     "kb_fasta_open": (c_int, [c_char_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "kb_fasta_fill": (c_int, [_P, _P, _P, _P, _P, _P]),
     "kb_fasta_close": (c_int, [_P]),

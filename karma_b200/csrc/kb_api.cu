@@ -88,6 +88,7 @@ extern "C" int kb_destroy(kb_ctx* c) {
     kb_free_exotic(c);
     cudaFree(c->d_rg_a); cudaFree(c->d_rg_b); cudaFree(c->d_rg_w); cudaFree(c->d_rg_shared);
     kb_links_free(c);
+    kb_knn_cache_free(c);
     if (c->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(c->pool); }
     free(c);
     return KB_OK;
@@ -159,25 +160,26 @@ extern "C" int kb_count(kb_ctx* ctx, int mode, const uint8_t* d_bases, const int
                         uint32_t* d_counts, int64_t ld, uint32_t* d_exotic, uint32_t* d_presence) {
     KB_CHECK_ARG(ctx && d_bases && d_offsets && d_counts, "null pointer");
     KbMode m;
-    int rc = kb_mode_describe(mode, &m);
+    const int track = (mode & KB_COUNT_NO_COLUMNS) ? 0 : 1;
+    int rc = kb_mode_describe(mode & ~KB_COUNT_NO_COLUMNS, &m);
     if (rc) return rc;
     KB_CHECK_ARG(n >= 0 && n < (1LL << 31) - 2, "contig count");
     KB_CHECK_ARG(ld >= m.cols && (ld % 4) == 0, "ld must be >= columns and a multiple of 4");
     KB_CHECK_ARG(((uintptr_t)d_bases % 16) == 0 && ((uintptr_t)d_counts % 16) == 0, "bases/counts must be 16-byte aligned");
     if (n == 0) return KB_OK;
     KB_CUDA(cudaSetDevice(ctx->device));
-    return kb_launch_count_kernels(ctx, m, d_bases, d_offsets, n, d_counts, ld, d_exotic, d_presence);
+    return kb_launch_count_kernels(ctx, m, d_bases, d_offsets, n, d_counts, ld, d_exotic, d_presence, track);
 }
 
 extern "C" int kb_count_stats(kb_ctx* ctx, int64_t* n_long, int64_t* exotic_total) {
     KB_CHECK_ARG(ctx, "ctx");
-    int32_t h[4] = {0, 0, 0, 0};
+    int32_t h[6] = {0, 0, 0, 0, 0, 0};      // K1 scratch: [2..3] exotic total, [4..5] (long contigs << 32) | chunks
     if (ctx->d_k1_scratch) {
         KB_CUDA(cudaSetDevice(ctx->device));
         KB_CUDA(cudaMemcpyAsync(h, ctx->d_k1_scratch, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         KB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    if (n_long) *n_long = h[1];
+    if (n_long) *n_long = h[5];
     if (exotic_total) { unsigned long long t; memcpy(&t, &h[2], 8); *exotic_total = (int64_t)t; }
     return KB_OK;
 }

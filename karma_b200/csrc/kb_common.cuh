@@ -37,6 +37,8 @@ struct kb_ctx {
     cudaMemPool_t pool;
     // tensor-map encoder (driver entry point, resolved lazily)
     void* encode_tiled;
+    // kNN plans and uploaded piece tables (kb_knn.cu)
+    void* knn_cache;
 };
 
 void kb_set_error(const char* fmt, ...);
@@ -78,9 +80,10 @@ int kb_mode_describe(int mode, KbMode* out);
 // internal launchers (defined in the per-kernel .cu files)
 int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases,
                             const int64_t* d_offsets, int64_t n, uint32_t* d_counts,
-                            int64_t ld, uint32_t* d_exotic, uint32_t* d_presence);
+                            int64_t ld, uint32_t* d_exotic, uint32_t* d_presence, int track_columns);
 
 void kb_links_free(kb_ctx* c);
+void kb_knn_cache_free(kb_ctx* c);
 // host-side file input shared by the FASTA and eq_classes parsers (kb_fasta.cu)
 int64_t kb_host_threads();
 int kb_host_read_file(const char* path, uint8_t** img, int64_t* size);

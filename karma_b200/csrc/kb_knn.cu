@@ -1,6 +1,6 @@
-// kb_knn.cu -- kNN driver: plan, key metadata, SIMT candidate kernel (K4-simt),
-// candidate merge + exact rerank (K5).  The tcgen05 candidate kernel is in
-// kb_knn_tc.cu.
+// kb_knn.cu -- kNN driver: plan, SIMT candidate kernel (K4-simt), candidate merge + exact rerank +
+// certification (K5), exact side path for rows beyond the tensor range (K4x) and the exact pass over
+// all keys for rows that could not be certified (K6).  The tcgen05 candidate kernel is in kb_knn_tc.cu.
 //
 // Replaces the neighbour search inside umap.UMAP(...).fit_transform at
 // /root/reference/karma/kmer.py:285-290 (euclidean metric, the point itself is
@@ -11,86 +11,271 @@
 // the fp32 norm expansion; K5 recomputes the kept candidates exactly:
 //     d2_ij = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2       (fp64, integer terms)
 #include "kb_knn.cuh"
+#include <cub/cub.cuh>
 #include <math.h>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
 
-int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64_t n_flag, KbKnnPlan* p) {
+// ---------------------------------------------------------------------------------------------
+// host: plan
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Band { int64_t t_lo, cnt; };
+
+struct Sched {
+    std::vector<std::vector<KbPiece>> per_worker;
+    std::vector<int32_t> slot_count;
+    int slots = 0;
+    int64_t n_pieces = 0;
+    double makespan = 0.0;
+};
+
+// unit (round r, group g): band (sd_g + r) % S, rotated to start at the diagonal tile when r == 0
+inline void unit_of(const KbKnnPlan& p, int64_t q_row0, int S, int r, int64_t g, KbPiece* u) {
+    int64_t td = (q_row0 + g * p.cl * p.bm) / p.bn;
+    if (td >= p.n_tiles) td = p.n_tiles - 1;
+    int sd = (int)((td * S) / p.n_tiles);
+    while (sd + 1 < S && (p.n_tiles * (sd + 1)) / S <= td) ++sd;
+    while (sd > 0 && (p.n_tiles * sd) / S > td) --sd;
+    const int s = (sd + r) % S;
+    const int64_t t_lo = (p.n_tiles * s) / S;
+    const int64_t cnt = (p.n_tiles * (s + 1)) / S - t_lo;
+    u->group = (int32_t)g; u->slot = 0; u->t_lo = (int32_t)t_lo; u->cnt = (int32_t)cnt;
+    u->shift = (r == 0) ? (int32_t)(td - t_lo) : 0;
+    u->i_lo = 0; u->i_cnt = (int32_t)cnt; u->pad = 0;
+}
+
+// kind 0: whole units dealt round-robin (round-major).  kind 1: every round's tile visits are cut into
+// `workers` equal contiguous ranges (group-major), so that all workers finish every band together.
+void build_sched(const KbKnnPlan& p, int64_t q_row0, int S, int kind, Sched* out) {
+    const int W = p.workers;
+    out->per_worker.assign(W, {});
+    out->slot_count.assign((size_t)p.groups, 0);
+    std::vector<double> load(W, 0.0);
+    int64_t u_lin = 0;
+    for (int r = 0; r < S; ++r) {
+        if (kind == 0) {
+            for (int64_t g = 0; g < p.groups; ++g, ++u_lin) {
+                KbPiece u; unit_of(p, q_row0, S, r, g, &u);
+                if (u.cnt == 0) continue;
+                u.slot = out->slot_count[g]++;
+                const int w = (int)(u_lin % W);
+                out->per_worker[w].push_back(u);
+                load[w] += u.i_cnt + 0.5;
+            }
+        } else {
+            int64_t V = 0;
+            for (int64_t g = 0; g < p.groups; ++g) { KbPiece u; unit_of(p, q_row0, S, r, g, &u); V += u.cnt; }
+            const int rot = (int)(((int64_t)r * W) / S);                 // decorrelates the floor/ceil pattern of the cuts
+            int64_t pos = 0;                                             // position in the round's sequence
+            int j = 0;                                                   // current range
+            int64_t j_end = (V * (j + 1)) / W;
+            for (int64_t g = 0; g < p.groups; ++g) {
+                KbPiece u; unit_of(p, q_row0, S, r, g, &u);
+                int64_t done = 0;
+                while (done < u.cnt) {
+                    while (pos >= j_end && j + 1 < W) { ++j; j_end = (V * (j + 1)) / W; }
+                    int64_t take = u.cnt - done;
+                    if (j + 1 < W && pos + take > j_end) take = j_end - pos;
+                    KbPiece pc = u;
+                    pc.i_lo = (int32_t)done; pc.i_cnt = (int32_t)take;
+                    pc.slot = out->slot_count[g]++;
+                    const int w = (j + rot) % W;
+                    out->per_worker[w].push_back(pc);
+                    load[w] += take + 0.5;
+                    done += take; pos += take;
+                }
+            }
+        }
+    }
+    out->slots = 0; out->n_pieces = 0; out->makespan = 0.0;
+    for (int64_t g = 0; g < p.groups; ++g) out->slots = std::max(out->slots, (int)out->slot_count[g]);
+    for (int w = 0; w < W; ++w) { out->n_pieces += (int64_t)out->per_worker[w].size(); out->makespan = std::max(out->makespan, load[w]); }
+}
+
+// sync_only: the key set does not fit in L2, so concurrent workers must sweep the same key tiles at the same
+// time (whole bands dealt round-robin, at least 2 bands); otherwise every band may also be cut into equal ranges.
+void choose_sched(const KbKnnPlan& p, int64_t q_row0, int min_bands, bool sync_only, Sched* best, int* best_S, int* best_kind) {
+    static const int cand[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64};
+    const int max_slots = KB_KNN_MAX_CAND / p.kp;
+    bool have = false;
+    const char* fs = getenv("KB_KNN_SPLITS");                            // experiments only
+    const char* fk = getenv("KB_KNN_SCHED");                             // experiments only: 0 round-robin units, 1 balanced cut
+    for (int S : cand) {
+        if (S > p.n_tiles || S > max_slots) break;
+        if (S < min_bands && S < p.n_tiles && S < max_slots) continue;
+        if (fs && atoi(fs) >= 1 && S != std::min<int64_t>(std::min<int64_t>(atoi(fs), p.n_tiles), max_slots)) continue;
+        for (int kind = 0; kind < 2; ++kind) {
+            if (fk ? atoi(fk) != kind : (sync_only && kind == 1)) continue;
+            Sched s;
+            build_sched(p, q_row0, S, kind, &s);
+            if (s.slots > max_slots) continue;
+            // fewer pieces win ties: every piece costs a list set-up and a write-back
+            if (!have || s.makespan < best->makespan * 0.995) { *best = std::move(s); *best_S = S; *best_kind = kind; have = true; }
+        }
+    }
+    if (!have) { build_sched(p, q_row0, 1, 0, best); *best_S = 1; *best_kind = 0; }
+}
+
+}  // namespace
+
+int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t dp, int32_t k, int64_t n_flag, KbKnnPlan* p) {
     if (k < 1 || nq < 1 || nk < 1 || k > nk) { kb_set_error("kNN: need 1 <= k <= nk and nq >= 1"); return KB_EINVAL; }
-    if (k > 24) { kb_set_error("kNN: n_neighbors > 24 not built (candidate lists are <= 32 wide)"); return KB_EUNSUPPORTED; }
+    memset(p, 0, sizeof(*p));
     p->impl = impl;
-    // candidates kept per (row, split): k plus a margin of >= 6 against fp32 ranking noise, in steps of 8
-    p->kp = (k <= 2) ? 8 : (k <= 10 ? 16 : (k <= 18 ? 24 : 32));
-    if (impl == KB_KNN_TC) { p->bm = 128; p->bn = 256; }
-    else { p->bm = 64; p->bn = 64; }
-    p->m_blocks = (nq + p->bm - 1) / p->bm;
-    p->n_tiles = (nk + p->bn - 1) / p->bn;
-    // Splits: units = (query-block groups) x S are dealt round-robin to the resident CTAs (tensor path:
-    // CTA pairs, so sm_count/2 workers and groups of 2 blocks).  Pick S in [1,32] minimising the makespan
-    // rounds(S) * tiles_per_unit(S), charging half a tile per unit for list setup and write-back.
-    int64_t cl = (impl == KB_KNN_TC && p->m_blocks >= 2) ? 2 : 1;
-    if (const char* f = getenv("KB_KNN_CLUSTER")) {             // experiments only: 1, 2 or 4 CTAs share every key tile
-        const int v = atoi(f);
-        if (impl == KB_KNN_TC && (v == 1 || v == 2 || v == 4) && p->m_blocks >= v) cl = v;
+    if (k > KB_KNN_K_MAX) {
+        // no candidate kernel: every row goes through the exact pass over all keys (kb_knn_fixup)
+        p->impl = 0; p->kp = 0; p->slots = 0;
+    } else {
+        // candidates kept per (row, slot): k plus a margin against fp32 ranking noise; K5 certifies every
+        // row against the margin actually available, so the margin is a matter of speed, not of correctness
+        p->kp = (k <= 2) ? 8 : (k <= 10 ? 16 : (k <= 18 ? 24 : (k <= 26 ? 32 : (k <= 42 ? 48 : 64))));
+        if (impl == KB_KNN_TC) { p->bm = 128; p->bn = 256; }
+        else { p->bm = 64; p->bn = 64; }
+        p->m_blocks = (nq + p->bm - 1) / p->bm;
+        p->n_tiles = (nk + p->bn - 1) / p->bn;
+        if (impl == KB_KNN_TC) {
+            int64_t cl = p->m_blocks >= 2 ? 2 : 1;
+            if (const char* f = getenv("KB_KNN_CLUSTER")) {         // experiments only: 1, 2 or 4 CTAs share every key tile
+                const int v = atoi(f);
+                if ((v == 1 || v == 2 || v == 4) && p->m_blocks >= v) cl = v;
+            }
+            p->cl = (int)cl;
+            p->groups = (p->m_blocks + cl - 1) / cl;
+            int64_t w = sm_count / cl > 0 ? sm_count / cl : 1;
+            if (cl == 4) w = std::min<int64_t>(w, 32);              // clusters of 4 live inside one GPC: fewer fit
+            const int64_t visits = p->groups * p->n_tiles;
+            if (w > visits) w = visits;
+            p->workers = (int)w;
+            Sched s; int S = 1, kind = 0;
+            double l2_mb = 120.0;                                   // B200: 126 MB of L2
+            if (const char* f = getenv("KB_KNN_L2_MB")) l2_mb = atof(f);   // experiments only
+            const bool sync_only = (double)nk * dp * 2.0 > l2_mb * 1e6;
+            const int min_bands = sync_only ? 2 : ((q_row0 > 0 || nq < nk) ? 4 : 1);
+            choose_sched(*p, q_row0, min_bands, sync_only, &s, &S, &kind);
+            p->slots = s.slots; p->bands = S; p->sched_kind = kind; p->n_pieces = s.n_pieces; p->makespan = s.makespan;
+        } else {
+            // SIMT: grid (m_blocks, slots); enough slots to fill the machine, at most 8 tiles per... keep it simple
+            p->cl = 1; p->groups = p->m_blocks; p->workers = 0;
+            int64_t want = ((int64_t)sm_count * 2 + p->m_blocks - 1) / p->m_blocks;
+            const int64_t max_slots = KB_KNN_MAX_CAND / p->kp < 32 ? KB_KNN_MAX_CAND / p->kp : 32;
+            if (want > max_slots) want = max_slots;
+            if (want > p->n_tiles) want = p->n_tiles;
+            if (want < 1) want = 1;
+            p->slots = (int)want; p->bands = (int)want;
+        }
     }
-    p->cl = (int)cl;
-    const int64_t groups = (p->m_blocks + cl - 1) / cl;
-    const int64_t workers = impl == KB_KNN_TC ? (sm_count / cl > 0 ? sm_count / cl : 1) : (int64_t)sm_count * 2;
-    int64_t want = 1; double best_cost = 1e300;
-    const int64_t max_splits = 512 / p->kp < 32 ? 512 / p->kp : 32;   // K5 merges at most 512 candidates per row
-    for (int64_t s_try = 1; s_try <= max_splits && s_try <= p->n_tiles; ++s_try) {
-        const int64_t rounds = (groups * s_try + workers - 1) / workers;
-        const int64_t per_unit = (p->n_tiles + s_try - 1) / s_try;
-        const double cost = (double)rounds * ((double)per_unit + 0.5);
-        if (cost < best_cost * 0.995) { best_cost = cost; want = s_try; }
-    }
-    if (const char* f = getenv("KB_KNN_SPLITS")) {              // experiments only
-        const int64_t v = atoll(f);
-        if (v >= 1) want = v < p->n_tiles ? v : p->n_tiles;
-        if (want > max_splits) want = max_splits;
-    }
-    p->splits = (int)want;
-    p->nk_pad = p->n_tiles * p->bn;
     int64_t off = 0;
-    p->off_colmeta = off; off += kb_round_up(p->nk_pad * (int64_t)sizeof(float2), 256);
-    p->off_score = off;   off += kb_round_up(nq * p->splits * p->kp * (int64_t)sizeof(float), 256);
-    p->off_idx = off;     off += kb_round_up(nq * p->splits * p->kp * (int64_t)sizeof(int32_t), 256);
+    const int64_t cand = nq * (int64_t)p->slots * p->kp;
+    p->off_score = off;   off += kb_round_up(cand * (int64_t)sizeof(float), 256);
+    p->off_idx = off;     off += kb_round_up(cand * (int64_t)sizeof(int32_t), 256);
     p->off_rowthr = off;  off += kb_round_up(nq * (int64_t)sizeof(int32_t), 256);
-    p->off_xidx = off;    off += n_flag > 0 ? kb_round_up(nq * p->kp * (int64_t)sizeof(int32_t), 256) : 0;
-    p->off_xd2 = off;     off += n_flag > 0 ? kb_round_up(nq * p->kp * (int64_t)sizeof(double), 256) : 0;
+    p->off_xidx = off;    off += (n_flag > 0 && p->kp) ? kb_round_up(nq * p->kp * (int64_t)sizeof(int32_t), 256) : 0;
+    p->off_xd2 = off;     off += (n_flag > 0 && p->kp) ? kb_round_up(nq * p->kp * (int64_t)sizeof(double), 256) : 0;
+    p->off_uncert = off;  off += kb_round_up((nq + 4) * (int64_t)sizeof(int32_t), 256);    // [0] count, [4..] rows
     p->total = off;
+    return KB_OK;
+}
+
+void kb_knn_plan_pieces(const KbKnnPlan& p, int64_t q_row0, KbPiece* pieces, int32_t* piece_start, int32_t* slot_count) {
+    Sched s;
+    build_sched(p, q_row0, p.bands, p.sched_kind, &s);      // same inputs -> the schedule the plan chose
+    int64_t at = 0;
+    for (int w = 0; w < p.workers; ++w) {
+        piece_start[w] = (int32_t)at;
+        for (const KbPiece& pc : s.per_worker[w]) pieces[at++] = pc;
+    }
+    piece_start[p.workers] = (int32_t)at;
+    for (int64_t g = 0; g < p.groups; ++g) slot_count[g] = s.slot_count[g];
+}
+
+// Per-context cache of plans and (tensor path) uploaded piece tables [pieces | piece_start | slot_count],
+// keyed by the plan inputs: planning walks every (band, group) unit, which is not free for a million rows.
+struct KbKnnEntry {
+    bool used;
+    int impl; int64_t nq, nk, q_row0, n_flag; int32_t k, dp; int sm;
+    KbKnnPlan plan;
+    void* d; int64_t off_start, off_slots;
+    uint64_t stamp;
+};
+struct KbKnnCache { KbKnnEntry e[8]; uint64_t clock; };
+
+void kb_knn_cache_free(kb_ctx* c) {
+    KbKnnCache* cache = reinterpret_cast<KbKnnCache*>(c->knn_cache);
+    if (!cache) return;
+    for (auto& t : cache->e) if (t.d) cudaFree(t.d);
+    free(cache);
+    c->knn_cache = nullptr;
+}
+
+static int plan_cached(kb_ctx* ctx, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t dp, int32_t k, int64_t n_flag, KbKnnEntry** out) {
+    if (!ctx->knn_cache) {
+        ctx->knn_cache = calloc(1, sizeof(KbKnnCache));
+        if (!ctx->knn_cache) { kb_set_error("out of host memory"); return KB_EINVAL; }
+    }
+    KbKnnCache* cache = reinterpret_cast<KbKnnCache*>(ctx->knn_cache);
+    KbKnnEntry* lru = &cache->e[0];
+    for (auto& t : cache->e) {
+        if (t.used && t.impl == impl && t.nq == nq && t.nk == nk && t.q_row0 == q_row0 && t.dp == dp && t.k == k && t.n_flag == n_flag &&
+            t.sm == ctx->sm_count) {
+            t.stamp = ++cache->clock; *out = &t; return KB_OK;
+        }
+        if (t.stamp < lru->stamp) lru = &t;
+    }
+    KbKnnPlan p;
+    int rc = kb_knn_plan(ctx->sm_count, impl, nq, nk, q_row0, dp, k, n_flag, &p);
+    if (rc) return rc;
+    if (lru->d) { KB_CUDA(cudaStreamSynchronize(ctx->stream)); KB_CUDA(cudaFree(lru->d)); lru->d = nullptr; }
+    lru->used = true; lru->impl = impl; lru->nq = nq; lru->nk = nk; lru->q_row0 = q_row0; lru->n_flag = n_flag; lru->k = k; lru->dp = dp;
+    lru->sm = ctx->sm_count; lru->plan = p; lru->stamp = ++cache->clock;
+    *out = lru;
+    return KB_OK;
+}
+
+// tensor path: build the piece table on the host and upload it synchronously (once per shape; warm up
+// before capturing a CUDA graph)
+static int table_cached(kb_ctx* ctx, KbKnnEntry* e) {
+    if (e->d) return KB_OK;
+    const KbKnnPlan& p = e->plan;
+    std::vector<KbPiece> pieces((size_t)p.n_pieces);
+    std::vector<int32_t> start((size_t)p.workers + 1), slots((size_t)p.groups);
+    kb_knn_plan_pieces(p, e->q_row0, pieces.data(), start.data(), slots.data());
+    const int64_t off_start = kb_round_up(p.n_pieces * (int64_t)sizeof(KbPiece), 256);
+    const int64_t off_slots = off_start + kb_round_up((p.workers + 1) * (int64_t)sizeof(int32_t), 256);
+    const int64_t bytes = off_slots + kb_round_up(p.groups * (int64_t)sizeof(int32_t), 256);
+    void* dv = nullptr;
+    KB_CUDA(cudaMalloc(&dv, (size_t)bytes));
+    uint8_t* d = reinterpret_cast<uint8_t*>(dv);
+    KB_CUDA(cudaMemcpy(d, pieces.data(), pieces.size() * sizeof(KbPiece), cudaMemcpyHostToDevice));
+    KB_CUDA(cudaMemcpy(d + off_start, start.data(), start.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    KB_CUDA(cudaMemcpy(d + off_slots, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    e->d = dv; e->off_start = off_start; e->off_slots = off_slots;
     return KB_OK;
 }
 
 namespace {
 
 __global__ void __launch_bounds__(256)
-k4_prep_colmeta(const kb_rowmeta* __restrict__ rowmeta, int64_t nk, int64_t nk_pad, float2* __restrict__ colmeta,
-                int32_t* __restrict__ row_thr, int64_t nq) {
+k4_init(int32_t* __restrict__ row_thr, int64_t nq, int32_t* __restrict__ uncert, int mark_all) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nq) row_thr[j] = 0x7f800000;                      // +inf as an ordered-int key
-    if (j >= nk_pad) return;
-    float2 cm;
-    kb_rowmeta m;
-    m.flags = 3;
-    if (j < nk) m = rowmeta[j];
-    if (!(m.flags & 3)) {
-        const double l = (double)m.key_len;
-        cm.x = (float)(-2.0 / l);
-        cm.y = (float)(m.sqnorm / (l * l));
-    } else {
-        cm.x = 0.f;
-        cm.y = __int_as_float(0x7f800000);                    // +inf: never a candidate
+    if (j < nq) {
+        row_thr[j] = 0x7f800000;                              // +inf as an ordered-int key
+        if (mark_all) uncert[4 + j] = (int32_t)j;
     }
-    colmeta[j] = cm;
+    if (j == 0) uncert[0] = mark_all ? (int32_t)nq : 0;
 }
 
 // ---------------------------------------------------------------------------
-// K4-simt: 64x64 score tiles on the CUDA cores (checker / fallback-free small path)
+// K4-simt: 64x64 score tiles on the CUDA cores (checker / small inputs)
+// dynamic shared memory: KP*64 floats + KP*64 ints (the lists)
 // ---------------------------------------------------------------------------
 template <int KP>
 __global__ void __launch_bounds__(256)
 k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
-        const float2* __restrict__ colmeta, const kb_rowmeta* __restrict__ rowmeta,
+        const kb_rowmeta* __restrict__ rowmeta,
         int64_t nk, int64_t q_row0, int64_t nq, int splits, int64_t n_tiles,
         float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
     constexpr int BM = 64, BN = 64, BK = 32;
@@ -101,8 +286,10 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
     float (*Bs)[BN + 4] = reinterpret_cast<float (*)[BN + 4]>(ab + BK * (BM + 4));
     float (*tile)[BN + 1] = reinterpret_cast<float (*)[BN + 1]>(ab);
     static_assert(BM * (BN + 1) <= 2 * BK * (BM + 4), "score tile must fit in the operand tiles");
-    __shared__ float ls[KP * BM];
-    __shared__ int32_t li[KP * BM];
+    extern __shared__ __align__(16) uint8_t dyn[];
+    float* ls = reinterpret_cast<float*>(dyn);
+    int32_t* li = reinterpret_cast<int32_t*>(dyn + KP * BM * sizeof(float));
+    __shared__ float2 cms[BN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t m0 = (int64_t)blockIdx.x * BM;
     const int s = blockIdx.y;
@@ -123,6 +310,7 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        if (tid < BN) cms[tid] = kb_load_cm(rowmeta, n0 + tid, nk);
         for (int k0 = 0; k0 < dp; k0 += BK) {
             uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
             if (m0 + lrow < nq) va = *reinterpret_cast<const uint4*>(op + (q_row0 + m0 + lrow) * ld + k0 + lseg);
@@ -156,7 +344,7 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
         __syncthreads();
         if (tid < BM) {
             for (int c = 0; c < BN; ++c) {
-                const float sc = kb_score(tile[tid][c], colmeta[n0 + c], my_len);
+                const float sc = kb_score(tile[tid][c], cms[c], my_len);
                 if (sc < list.bound) list.insert(tid, sc, (int32_t)(n0 + c));
             }
         }
@@ -169,32 +357,42 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
 }
 
 // ---------------------------------------------------------------------------
-// K5: merge the per-split candidate lists by score, rerank exactly, order, emit.
-// One warp per query row.
+// K5: merge the per-slot candidate lists by score, rerank exactly, order, certify, emit.
+// One warp per query row.  Lane l holds merged candidates l and l+32 (KP <= 64).
 // ---------------------------------------------------------------------------
+struct K5Peers { int32_t n; int32_t* const* idx; float* const* dist; };
+
 template <int KP>
 __global__ void __launch_bounds__(256)
 k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
-                const kb_rowmeta* __restrict__ rowmeta, int64_t q_row0, int64_t nq, int splits, int32_t k,
+                const kb_rowmeta* __restrict__ rowmeta, int64_t q_row0, int64_t nq, int slots, int32_t k,
+                const int32_t* __restrict__ slot_count, int rows_per_group,
                 const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                 const int32_t* __restrict__ extra_idx, const double* __restrict__ extra_d2,
-                int32_t* __restrict__ out_idx, float* __restrict__ out_dist, double* __restrict__ out_d2) {
-    constexpr int MAXC = 16;                                  // splits*KP <= 32*MAXC
+                int32_t* __restrict__ out_idx, float* __restrict__ out_dist, double* __restrict__ out_d2,
+                int32_t* __restrict__ uncert, K5Peers peers) {
+    constexpr int MAXC = KB_KNN_MAX_CAND / 32;               // slots*KP <= 32*MAXC
+    constexpr int NS = (KP + 31) / 32;                       // merged candidates per lane
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    const int total = splits * KP;
+    const int my_slots = slot_count ? slot_count[q / rows_per_group] : slots;
+    const int total = my_slots * KP;
     const float INF = __int_as_float(0x7f800000);
     // ---- 1. every lane takes candidates lane, lane+32, ... ; KP rounds of warp arg-min
     float cs[MAXC]; int32_t ci[MAXC];
+    const int64_t cbase = q * (int64_t)slots * KP;
 #pragma unroll
     for (int u = 0; u < MAXC; ++u) {
         const int e = lane + 32 * u;
-        if (e < total) { cs[u] = cand_score[q * total + e]; ci[u] = cand_idx[q * total + e]; }
+        if (e < total) { cs[u] = cand_score[cbase + e]; ci[u] = cand_idx[cbase + e]; }
         else { cs[u] = INF; ci[u] = -1; }
         if (ci[u] < 0) cs[u] = INF;
     }
-    int32_t my_idx = -1;                                      // lane e ends up holding merged candidate e
+    int32_t my_idx[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) my_idx[s] = -1;
+    float m_last = INF;                                       // score of the KP-th merged candidate (+inf: fewer exist)
     for (int r = 0; r < KP; ++r) {
         float best = INF; int32_t bidx = 0x7fffffff; int bu = -1;
 #pragma unroll
@@ -213,19 +411,43 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 #pragma unroll
             for (int u = 0; u < MAXC; ++u) if (u == bu) ci[u] = -1;   // consume
         }
-        if (lane == r) my_idx = wi;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) if (r == lane + 32 * s) my_idx[s] = wi;
+        if (r == KP - 1) m_last = wb;
     }
     // ---- 2. exact-side-path extras (rows the tensor path cannot score exactly): lane e also
-    //         holds extra candidate e with its exact d2.  A flagged QUERY keeps only extras.
+    //         holds extra candidates e, e+32 with their exact d2.  A flagged QUERY keeps only extras.
     const int32_t self = (int32_t)(q_row0 + q);
-    int32_t x_idx = -1; double x_d2 = 0.0;
+    const kb_rowmeta mq = rowmeta[self];
+    const bool q_flagged = (mq.flags & 3) != 0;
+    int32_t x_idx[NS]; double x_d2[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { x_idx[s] = -1; x_d2[s] = 0.0; }
+    int n_extra = 0; double x_max = 0.0;
     if (extra_idx) {
-        if (lane < KP) { x_idx = extra_idx[q * KP + lane]; x_d2 = extra_d2[q * KP + lane]; }
-        if (rowmeta[self].flags & 3) my_idx = -1;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int e = lane + 32 * s;
+            if (e < KP) { x_idx[s] = extra_idx[q * KP + e]; x_d2[s] = extra_d2[q * KP + e]; }
+            n_extra += __popc(__ballot_sync(0xffffffffu, x_idx[s] >= 0));
+            double xm = x_idx[s] >= 0 ? x_d2[s] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) xm = fmax(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+            x_max = fmax(x_max, xm);
+        }
+        if (q_flagged) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) my_idx[s] = -1;
+        }
     }
-    // self must be a candidate: it replaces the last slot if it is missing
-    const unsigned has_self = __ballot_sync(0xffffffffu, my_idx == self || x_idx == self);
-    if (!has_self && lane == KP - 1) my_idx = self;
+    // self must be a candidate: it replaces the last merged slot if it is missing
+    bool has_self_l = false;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) has_self_l |= (my_idx[s] == self || x_idx[s] == self);
+    const unsigned has_self = __ballot_sync(0xffffffffu, has_self_l);
+    if (!has_self) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) if (lane + 32 * s == KP - 1) my_idx[s] = self;
+    }
     // ---- 3. exact distances: all lanes cooperate on one candidate at a time.
     //   sum_c (a_c*lj - b_c*lq)^2 = lj^2*n_q + lq^2*n_j - 2*lj*lq*g,  g = sum_c a_c*b_c.
     //   Rows that reach this point are unflagged: counts <= 2048 and n < 2^24, hence
@@ -233,71 +455,130 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
     //   exactly representable integer -- the fp32 FMA chain IS the exact integer Gram entry.
     //   The three terms are exact integers in fp64 (< 2^53), so d2 has one rounding (the division).
     const __half* qrow = op + (int64_t)self * ld;
-    const kb_rowmeta mq = rowmeta[self];
     const double lq = (double)mq.key_len;
-    double my_d2 = 0.0;
-    for (int e = 0; e < KP; ++e) {
-        const int32_t j = __shfl_sync(0xffffffffu, my_idx, e);
-        if (j < 0 || j == self) continue;                     // d2(self) = 0 exactly
-        const __half* krow = op + (int64_t)j * ld;
-        float g0 = 0.f, g1 = 0.f;
-        for (int c = 8 * lane; c < dp; c += 256) {
-            const uint4 a = *reinterpret_cast<const uint4*>(qrow + c);
-            const uint4 b = *reinterpret_cast<const uint4*>(krow + c);
-            const __half2* ha = reinterpret_cast<const __half2*>(&a);
-            const __half2* hb = reinterpret_cast<const __half2*>(&b);
+    double my_d2[NS];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const float2 fa = __half22float2(ha[x]), fb = __half22float2(hb[x]);
-                g0 = fmaf(fa.x, fb.x, g0);
-                g1 = fmaf(fa.y, fb.y, g1);
+    for (int s = 0; s < NS; ++s) my_d2[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        for (int e = 0; e < 32 && e + 32 * s < KP; ++e) {
+            const int32_t j = __shfl_sync(0xffffffffu, my_idx[s], e);
+            if (j < 0 || j == self) continue;                 // d2(self) = 0 exactly
+            const __half* krow = op + (int64_t)j * ld;
+            float g0 = 0.f, g1 = 0.f;
+            for (int c = 8 * lane; c < dp; c += 256) {
+                const uint4 a = *reinterpret_cast<const uint4*>(qrow + c);
+                const uint4 b = *reinterpret_cast<const uint4*>(krow + c);
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const float2 fa = __half22float2(ha[x]), fb = __half22float2(hb[x]);
+                    g0 = fmaf(fa.x, fb.x, g0);
+                    g1 = fmaf(fa.y, fb.y, g1);
+                }
             }
-        }
-        float g = g0 + g1;
-        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-        if (lane == e) {
-            const kb_rowmeta mj = rowmeta[j];
-            const double lj = (double)mj.key_len;
-            const double num = lj * lj * mq.sqnorm + lq * lq * mj.sqnorm - 2.0 * (lj * lq) * (double)g;
-            my_d2 = num / ((lq * lj) * (lq * lj));
+            float g = g0 + g1;
+            for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+            if (lane == e) {
+                const kb_rowmeta mj = rowmeta[j];
+                const double lj = (double)mj.key_len;
+                const double num = lj * lj * mq.sqnorm + lq * lq * mj.sqnorm - 2.0 * (lj * lq) * (double)g;
+                my_d2[s] = num / ((lq * lj) * (lq * lj));
+            }
         }
     }
     // ---- 4. order: self first, then (d2, idx); rank by counting over both item sets
-    const bool valid_a = (lane < KP) && (my_idx >= 0);
-    const bool valid_b = (lane < KP) && (x_idx >= 0);
-    const double key_a = (my_idx == self) ? -1.0 : my_d2;
-    const double key_b = (x_idx == self) ? -1.0 : x_d2;
-    int rank_a = 0, rank_b = 0;
-    for (int e = 0; e < KP; ++e) {
-        const int32_t oj = __shfl_sync(0xffffffffu, my_idx, e);
-        const double od = __shfl_sync(0xffffffffu, key_a, e);
-        const int32_t xj = __shfl_sync(0xffffffffu, x_idx, e);
-        const double xd = __shfl_sync(0xffffffffu, key_b, e);
-        if (oj >= 0) {
-            if (e != lane && (od < key_a || (od == key_a && oj < my_idx))) ++rank_a;
-            if (od < key_b || (od == key_b && oj < x_idx)) ++rank_b;
-        }
-        if (xj >= 0) {
-            if (xd < key_a || (xd == key_a && xj < my_idx)) ++rank_a;
-            if (e != lane && (xd < key_b || (xd == key_b && xj < x_idx))) ++rank_b;
+    bool valid_a[NS], valid_b[NS]; double key_a[NS], key_b[NS]; int rank_a[NS], rank_b[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const bool in = lane + 32 * s < KP;
+        valid_a[s] = in && my_idx[s] >= 0;
+        valid_b[s] = in && x_idx[s] >= 0;
+        key_a[s] = (my_idx[s] == self) ? -1.0 : my_d2[s];
+        key_b[s] = (x_idx[s] == self) ? -1.0 : x_d2[s];
+        rank_a[s] = 0; rank_b[s] = 0;
+    }
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        for (int e = 0; e < 32 && e + 32 * t < KP; ++e) {
+            const int32_t oj = __shfl_sync(0xffffffffu, my_idx[t], e);
+            const double od = __shfl_sync(0xffffffffu, key_a[t], e);
+            const int32_t xj = __shfl_sync(0xffffffffu, x_idx[t], e);
+            const double xd = __shfl_sync(0xffffffffu, key_b[t], e);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const bool same = (s == t) && (e == lane);
+                if (oj >= 0) {
+                    if (!same && (od < key_a[s] || (od == key_a[s] && oj < my_idx[s]))) ++rank_a[s];
+                    if (od < key_b[s] || (od == key_b[s] && oj < x_idx[s])) ++rank_b[s];
+                }
+                if (xj >= 0) {
+                    if (xd < key_a[s] || (xd == key_a[s] && xj < my_idx[s])) ++rank_a[s];
+                    if (!same && (xd < key_b[s] || (xd == key_b[s] && xj < x_idx[s]))) ++rank_b[s];
+                }
+            }
         }
     }
-    if (valid_a && rank_a < k) {
-        out_idx[q * k + rank_a] = my_idx;
-        out_dist[q * k + rank_a] = (float)sqrt(my_d2);
-        if (out_d2) out_d2[q * k + rank_a] = my_d2;
+    int n_valid = 0;
+    double dk = -2.0;                                          // d2 key of the k-th neighbour
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        n_valid += __popc(__ballot_sync(0xffffffffu, valid_a[s])) + __popc(__ballot_sync(0xffffffffu, valid_b[s]));
+        if (valid_a[s] && rank_a[s] == k - 1) dk = key_a[s];
+        if (valid_b[s] && rank_b[s] == k - 1) dk = key_b[s];
     }
-    if (valid_b && rank_b < k) {
-        out_idx[q * k + rank_b] = x_idx;
-        out_dist[q * k + rank_b] = (float)sqrt(x_d2);
-        if (out_d2) out_d2[q * k + rank_b] = x_d2;
+    for (int o = 16; o > 0; o >>= 1) dk = fmax(dk, __shfl_xor_sync(0xffffffffu, dk, o));
+    const int64_t grow = (int64_t)self * k;                   // row in the peers' gathered arrays
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (valid_a[s] && rank_a[s] < k) {
+            const float dd = (float)sqrt(my_d2[s]);
+            out_idx[q * k + rank_a[s]] = my_idx[s];
+            out_dist[q * k + rank_a[s]] = dd;
+            if (out_d2) out_d2[q * k + rank_a[s]] = my_d2[s];
+            for (int pr = 0; pr < peers.n; ++pr) { peers.idx[pr][grow + rank_a[s]] = my_idx[s]; peers.dist[pr][grow + rank_a[s]] = dd; }
+        }
+        if (valid_b[s] && rank_b[s] < k) {
+            const float dd = (float)sqrt(x_d2[s]);
+            out_idx[q * k + rank_b[s]] = x_idx[s];
+            out_dist[q * k + rank_b[s]] = dd;
+            if (out_d2) out_d2[q * k + rank_b[s]] = x_d2[s];
+            for (int pr = 0; pr < peers.n; ++pr) { peers.idx[pr][grow + rank_b[s]] = x_idx[s]; peers.dist[pr][grow + rank_b[s]] = dd; }
+        }
     }
     // fewer valid candidates than k -> mark the rest
-    const int n_valid = __popc(__ballot_sync(0xffffffffu, valid_a)) + __popc(__ballot_sync(0xffffffffu, valid_b));
-    if (lane >= n_valid && lane < k) {
-        out_idx[q * k + lane] = -1;
-        out_dist[q * k + lane] = INF;
-        if (out_d2) out_d2[q * k + lane] = (double)INF;
+    for (int e = n_valid + lane; e < k; e += 32) {
+        out_idx[q * k + e] = -1;
+        out_dist[q * k + e] = INF;
+        if (out_d2) out_d2[q * k + e] = (double)INF;
+        for (int pr = 0; pr < peers.n; ++pr) { peers.idx[pr][grow + e] = -1; peers.dist[pr][grow + e] = INF; }
+    }
+    // ---- 5. certificate.  Every key that is not among the merged candidates has an fp32 score >= m_last.
+    //   s_k = exact score of the k-th neighbour (s = l_q*d2 - n_q/l_q); a key j with a_j = l_q*n_j/l_j^2 > Y^2,
+    //   Y = c + sqrt(c^2 + s_k), c^2 = n_q/l_q, has an exact score above s_k whatever its Gram entry is
+    //   (Cauchy-Schwarz); for all other keys the fp32 evaluation error is at most E = 2^-22*(Y^2 + 2cY).
+    //   Flagged keys only come through the extras (exact): if that list is full, the k-th neighbour must
+    //   not be farther than its last entry.
+    if (lane == 0) {
+        bool ok = true;
+        if (!q_flagged) {
+            if (n_valid < k) ok = (m_last == INF);
+            else if (m_last != INF) {
+                const double d2k = dk < 0.0 ? 0.0 : dk;
+                const double c2 = mq.sqnorm / lq;
+                const double sk = lq * d2k - c2;
+                const double c = sqrt(c2);
+                const double Y = c + sqrt(fmax(c2 + sk, 0.0));
+                const double E = 2.384185791015625e-07 * (Y * Y + 2.0 * c * Y);
+                ok = sk + 2.0 * E < (double)m_last;
+            }
+            if (ok && n_extra >= KP && n_valid >= k && dk > x_max) ok = false;
+        }
+        if (!ok) {
+            const int pos = atomicAdd(&uncert[0], 1);
+            uncert[4 + pos] = (int32_t)q;
+        }
     }
 }
 
@@ -345,8 +626,7 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
         } else {
             for (int c = threadIdx.x; c < dp; c += 256) qrow[c] = (uint32_t)__half2float(op[(int64_t)self * ld + c]);
         }
-        if (lane < KP) { wl_d[warp][lane] = DINF; wl_i[warp][lane] = -1; }
-        if (KP > 32 && lane + 32 < KP) { wl_d[warp][lane + 32] = DINF; wl_i[warp][lane + 32] = -1; }
+        for (int e = lane; e < KP; e += 32) { wl_d[warp][e] = DINF; wl_i[warp][e] = -1; }
         __syncthreads();
         const double lq = (double)mq.key_len;
         const int64_t n_keys = q_flagged ? nk : (int64_t)n_flag;
@@ -416,14 +696,147 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
     }
 }
 
+// ---------------------------------------------------------------------------
+// K6: exact pass over ALL keys for the rows K5 could not certify (and for every row when
+// k > KB_KNN_K_MAX).  k6_dist: one CTA per (4 listed queries, chunk of keys); a warp takes one key
+// row at a time and produces its exact d2 to the 4 queries.  The rows are then ordered by a
+// segmented radix sort on (d2, key index); k6_emit writes the first k of every segment.
+// ---------------------------------------------------------------------------
+constexpr int K6_QB = 4;
+
+__global__ void __launch_bounds__(256)
+k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta* __restrict__ rowmeta,
+        int64_t nk, int64_t q_row0, const int32_t* __restrict__ rows, int64_t row_lo, int64_t n_rows,
+        const int32_t* __restrict__ flag_rows, const uint32_t* __restrict__ flag_counts, int64_t ld_fc,
+        int32_t fc_cols, int32_t n_flag, int64_t keys_per_cta,
+        double* __restrict__ d2_out, int32_t* __restrict__ idx_out) {
+    extern __shared__ __align__(16) float qs[];               // K6_QB x dp query counts as floats (exact: <= 2^24)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * K6_QB;           // first listed row of this CTA (relative to row_lo)
+    const double DINF = __longlong_as_double(0x7ff0000000000000LL);
+    int32_t selfs[K6_QB]; double lqs[K6_QB], nqs[K6_QB]; bool qf[K6_QB], live[K6_QB];
+#pragma unroll
+    for (int i = 0; i < K6_QB; ++i) {
+        live[i] = b0 + i < n_rows;
+        selfs[i] = live[i] ? (int32_t)(q_row0 + rows[row_lo + b0 + i]) : 0;
+        const kb_rowmeta m = rowmeta[selfs[i]];
+        lqs[i] = (double)m.key_len; nqs[i] = m.sqnorm; qf[i] = (m.flags & 3) != 0;
+        if (qf[i]) {
+            const int slot = find_slot(flag_rows, n_flag, selfs[i]);
+            for (int c = threadIdx.x; c < dp; c += 256)
+                qs[i * dp + c] = (slot >= 0 && c < fc_cols) ? (float)flag_counts[(int64_t)slot * ld_fc + c] : 0.f;
+        } else {
+            for (int c = threadIdx.x; c < dp; c += 256) qs[i * dp + c] = __half2float(op[(int64_t)selfs[i] * ld + c]);
+        }
+    }
+    __syncthreads();
+    const int64_t j_lo = (int64_t)blockIdx.y * keys_per_cta;
+    const int64_t j_hi = (j_lo + keys_per_cta < nk) ? j_lo + keys_per_cta : nk;
+    for (int64_t j = j_lo + warp; j < j_hi; j += 8) {
+        const kb_rowmeta mj = rowmeta[j];
+        const bool kf = (mj.flags & 3) != 0;
+        const bool pad = (mj.flags & 8) != 0;
+        const double lj = (double)mj.key_len;
+        double acc[K6_QB];
+#pragma unroll
+        for (int i = 0; i < K6_QB; ++i) acc[i] = 0.0;
+        bool any_f = kf;
+#pragma unroll
+        for (int i = 0; i < K6_QB; ++i) any_f |= qf[i];
+        if (!pad) {
+            if (any_f) {
+                // fp64 from the true counts: sum_c (a_c*lj - b_c*lq)^2
+                const int slot = kf ? find_slot(flag_rows, n_flag, (int32_t)j) : -1;
+                for (int c = lane; c < dp; c += 32) {
+                    const double b = kf ? ((slot >= 0 && c < fc_cols) ? (double)flag_counts[(int64_t)slot * ld_fc + c] : 0.0)
+                                        : (double)__half2float(op[j * ld + c]);
+#pragma unroll
+                    for (int i = 0; i < K6_QB; ++i) {
+                        const double d = (double)qs[i * dp + c] * lj - b * lqs[i];
+                        acc[i] = fma(d, d, acc[i]);
+                    }
+                }
+            } else {
+                // unflagged x unflagged: the fp32 dot product is the exact integer Gram entry
+                float g[K6_QB];
+#pragma unroll
+                for (int i = 0; i < K6_QB; ++i) g[i] = 0.f;
+                const __half* krow = op + j * ld;
+                for (int c = 8 * lane; c < dp; c += 256) {
+                    const uint4 b = *reinterpret_cast<const uint4*>(krow + c);
+                    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const float2 fb = __half22float2(hb[x]);
+#pragma unroll
+                        for (int i = 0; i < K6_QB; ++i) {
+                            g[i] = fmaf(qs[i * dp + c + 2 * x], fb.x, g[i]);
+                            g[i] = fmaf(qs[i * dp + c + 2 * x + 1], fb.y, g[i]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < K6_QB; ++i) acc[i] = (double)g[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < K6_QB; ++i)
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < K6_QB; ++i) {
+                if (!live[i]) continue;
+                double d2;
+                if (pad) d2 = DINF;
+                else if ((int32_t)j == selfs[i]) d2 = -1.0;                   // the point itself sorts first
+                else if (any_f) d2 = acc[i] / ((lqs[i] * lj) * (lqs[i] * lj));
+                else {
+                    const double num = lj * lj * nqs[i] + lqs[i] * lqs[i] * mj.sqnorm - 2.0 * (lj * lqs[i]) * acc[i];
+                    d2 = num / ((lqs[i] * lj) * (lqs[i] * lj));
+                }
+                d2_out[(b0 + i) * nk + j] = d2;
+                idx_out[(b0 + i) * nk + j] = (int32_t)j;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k6_emit(const double* __restrict__ d2_sorted, const int32_t* __restrict__ idx_sorted, int64_t nk,
+        const int32_t* __restrict__ rows, int64_t row_lo, int64_t n_rows, int32_t k,
+        int32_t* __restrict__ out_idx, float* __restrict__ out_dist, double* __restrict__ out_d2) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * k) return;
+    const int64_t b = t / k; const int e = (int)(t % k);
+    const int64_t q = rows[row_lo + b];
+    double d2 = d2_sorted[b * nk + e];
+    int32_t j = idx_sorted[b * nk + e];
+    if (d2 < 0.0) d2 = 0.0;                                    // self
+    if (isinf(d2)) j = -1;
+    out_idx[q * k + e] = j;
+    out_dist[q * k + e] = (float)sqrt(d2);
+    if (out_d2) out_d2[q * k + e] = d2;
+}
+
+__global__ void k6_segments(int64_t nk, int64_t n, int64_t* __restrict__ seg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) seg[i] = i * nk;
+}
+
 template <int KP>
 int run_simt(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp,
              const kb_rowmeta* rowmeta, int64_t nk, int64_t q_row0, int64_t nq, uint8_t* ws) {
-    dim3 grid((unsigned)p.m_blocks, (unsigned)p.splits);
-    k4_simt<KP><<<grid, 256, 0, ctx->stream>>>(op, ld, dp, reinterpret_cast<const float2*>(ws + p.off_colmeta),
-                                              rowmeta, nk, q_row0, nq, p.splits, p.n_tiles,
-                                              reinterpret_cast<float*>(ws + p.off_score),
-                                              reinterpret_cast<int32_t*>(ws + p.off_idx));
+    dim3 grid((unsigned)p.m_blocks, (unsigned)p.slots);
+    auto kern = k4_simt<KP>;
+    const size_t smem = (size_t)KP * 64 * 8;
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device & 15] = true;
+    }
+    kern<<<grid, 256, smem, ctx->stream>>>(op, ld, dp, rowmeta, nk, q_row0, nq, p.slots, p.n_tiles,
+                                           reinterpret_cast<float*>(ws + p.off_score),
+                                           reinterpret_cast<int32_t*>(ws + p.off_idx));
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;
@@ -432,13 +845,14 @@ int run_simt(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int3
 template <int KP>
 int run_rerank(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp,
                const kb_rowmeta* rowmeta, int64_t q_row0, int64_t nq, int32_t k, uint8_t* ws, bool extras,
-               int32_t* d_idx, float* d_dist, double* d_d2) {
+               const int32_t* slot_count, int32_t* d_idx, float* d_dist, double* d_d2, K5Peers peers) {
     const int64_t grid = (nq + 7) / 8;
     k5_merge_rerank<KP><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-        op, ld, dp, rowmeta, q_row0, nq, p.splits, k, reinterpret_cast<const float*>(ws + p.off_score),
-        reinterpret_cast<const int32_t*>(ws + p.off_idx),
+        op, ld, dp, rowmeta, q_row0, nq, p.slots, k, slot_count, p.bm * p.cl,
+        reinterpret_cast<const float*>(ws + p.off_score), reinterpret_cast<const int32_t*>(ws + p.off_idx),
         extras ? reinterpret_cast<const int32_t*>(ws + p.off_xidx) : nullptr,
-        extras ? reinterpret_cast<const double*>(ws + p.off_xd2) : nullptr, d_idx, d_dist, d_d2);
+        extras ? reinterpret_cast<const double*>(ws + p.off_xd2) : nullptr, d_idx, d_dist, d_d2,
+        reinterpret_cast<int32_t*>(ws + p.off_uncert), peers);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;
@@ -460,18 +874,94 @@ int run_exact(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int
     return KB_OK;
 }
 
+#define KB_KP_SWITCH(kp, CALL)                 \
+    switch (kp) {                              \
+        case 8: rc = CALL(8); break;           \
+        case 16: rc = CALL(16); break;         \
+        case 24: rc = CALL(24); break;         \
+        case 32: rc = CALL(32); break;         \
+        case 48: rc = CALL(48); break;         \
+        default: rc = CALL(64); break;         \
+    }
+
+int check_args(kb_ctx* ctx, int& impl, int32_t k, const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
+               const kb_rowmeta* d_rowmeta, int64_t nk, int64_t q_row0, int64_t nq, const int32_t* d_flag_rows,
+               const uint32_t* d_flag_counts, int64_t ld_flag_counts, int32_t flag_cols, int64_t n_flag,
+               int32_t* d_idx, float* d_dist, void* d_workspace, int64_t workspace_bytes, KbKnnEntry** ent) {
+    KB_CHECK_ARG(ctx && d_operand && d_rowmeta && d_idx && d_dist && d_workspace, "null pointer");
+    KB_CHECK_ARG(d_cols_padded > 0 && (d_cols_padded % 64) == 0 && ld_operand >= d_cols_padded && (ld_operand % 8) == 0,
+                 "operand columns must be padded to a multiple of 64");
+    KB_CHECK_ARG(((uintptr_t)d_operand % 16) == 0, "operand must be 16-byte aligned");
+    KB_CHECK_ARG(q_row0 >= 0 && nq >= 1 && q_row0 + nq <= nk, "query rows must be a sub-range of the keys");
+    KB_CHECK_ARG(nk < (1LL << 31), "more than 2^31 keys");
+    if (impl == KB_KNN_AUTO) impl = (nk >= 512) ? KB_KNN_TC : KB_KNN_SIMT;
+    KB_CHECK_ARG(impl == KB_KNN_SIMT || impl == KB_KNN_TC, "impl");
+    KB_CHECK_ARG(n_flag >= 0 && n_flag < (1LL << 31) && (n_flag == 0 || (d_flag_rows && d_flag_counts && ld_flag_counts >= flag_cols)),
+                 "flagged-row side inputs");
+    int rc = plan_cached(ctx, impl, nq, nk, q_row0, d_cols_padded, k, n_flag, ent);
+    if (rc) return rc;
+    const KbKnnPlan* p = &(*ent)->plan;
+    if (p->slots * p->kp > KB_KNN_MAX_CAND) { kb_set_error("internal: too many candidates per row"); return KB_EUNSUPPORTED; }
+    if (workspace_bytes < p->total) { kb_set_error("kNN workspace: need %lld bytes, got %lld", (long long)p->total, (long long)workspace_bytes); return KB_EWORKSPACE; }
+    KB_CHECK_ARG(((uintptr_t)d_workspace % 256) == 0, "workspace must be 256-byte aligned");
+    return KB_OK;
+}
+
 }  // namespace
 
-extern "C" int64_t kb_knn_workspace_bytes(int64_t nq, int64_t nk, int32_t k, int impl, int64_t n_flag) {
-    KbKnnPlan p;
+extern "C" int64_t kb_knn_workspace_bytes(kb_ctx* ctx, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k, int impl, int64_t n_flag) {
     int64_t best = 0;
     for (int im = KB_KNN_SIMT; im <= KB_KNN_TC; ++im) {
         if (impl != KB_KNN_AUTO && impl != im) continue;
-        int rc = kb_knn_plan(148, im, nq, nk, k, n_flag, &p);
-        if (rc) return rc;
+        KbKnnPlan p;
+        if (ctx) {
+            KbKnnEntry* ent = nullptr;
+            int rc = plan_cached(ctx, im, nq, nk, q_row0, d_cols_padded, k, n_flag, &ent);
+            if (rc) return rc;
+            p = ent->plan;
+        } else {
+            int rc = kb_knn_plan(148, im, nq, nk, q_row0, d_cols_padded, k, n_flag, &p);   // no context: a 148-SM B200
+            if (rc) return rc;
+        }
         if (p.total > best) best = p.total;
     }
     return best;
+}
+
+// host-only view of the schedule (tests, diagnostics): fills out[0..7] = kp, slots, bands, kind, workers, pieces,
+// makespan*1000, ideal*1000 (tile visits per worker)
+extern "C" int kb_knn_plan_info(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k, int64_t* out) {
+    KbKnnPlan p;
+    int rc = kb_knn_plan(sm_count, impl, nq, nk, q_row0, d_cols_padded, k, 0, &p);
+    if (rc) return rc;
+    out[0] = p.kp; out[1] = p.slots; out[2] = p.bands; out[3] = p.sched_kind; out[4] = p.workers; out[5] = p.n_pieces;
+    out[6] = (int64_t)(p.makespan * 1000.0);
+    out[7] = p.workers ? (int64_t)(1000.0 * (double)p.groups * (double)p.n_tiles / p.workers) : 0;
+    return KB_OK;
+}
+
+// host-only: the piece table itself, for coverage checks.  pieces: int32[n_pieces*8] (KbPiece), piece_start:
+// int32[workers+1], slot_count: int32[groups]
+extern "C" int kb_knn_plan_table(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k,
+                                 int32_t* pieces, int32_t* piece_start, int32_t* slot_count) {
+    KbKnnPlan p;
+    int rc = kb_knn_plan(sm_count, impl, nq, nk, q_row0, d_cols_padded, k, 0, &p);
+    if (rc) return rc;
+    if (p.impl != KB_KNN_TC) { kb_set_error("piece tables belong to the tensor kernel"); return KB_EINVAL; }
+    kb_knn_plan_pieces(p, q_row0, reinterpret_cast<KbPiece*>(pieces), piece_start, slot_count);
+    return KB_OK;
+}
+
+extern "C" int kb_knn_uncertified_ptr(kb_ctx* ctx, int64_t nq, int64_t nk, int64_t q_row0, int32_t d_cols_padded, int32_t k, int impl, int64_t n_flag,
+                                      void* d_workspace, const uint32_t** d_count) {
+    KB_CHECK_ARG(ctx && d_workspace && d_count, "null pointer");
+    if (impl == KB_KNN_AUTO) impl = (nk >= 512) ? KB_KNN_TC : KB_KNN_SIMT;
+    KbKnnEntry* ent = nullptr;
+    int rc = plan_cached(ctx, impl, nq, nk, q_row0, d_cols_padded, k, n_flag, &ent);
+    if (rc) return rc;
+    const KbKnnPlan& p = ent->plan;
+    *d_count = reinterpret_cast<const uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + p.off_uncert);
+    return KB_OK;
 }
 
 extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
@@ -481,64 +971,144 @@ extern "C" int kb_knn(kb_ctx* ctx, int impl, int32_t k,
                       const int32_t* d_flag_rows, const uint32_t* d_flag_counts, int64_t ld_flag_counts,
                       int32_t flag_cols, int64_t n_flag,
                       int32_t* d_idx, float* d_dist, double* d_d2,
-                      void* d_workspace, int64_t workspace_bytes) {
-    KB_CHECK_ARG(ctx && d_operand && d_rowmeta && d_idx && d_dist && d_workspace, "null pointer");
-    KB_CHECK_ARG(d_cols_padded > 0 && (d_cols_padded % 64) == 0 && ld_operand >= d_cols_padded && (ld_operand % 8) == 0,
-                 "operand columns must be padded to a multiple of 64");
-    KB_CHECK_ARG(((uintptr_t)d_operand % 16) == 0, "operand must be 16-byte aligned");
-    KB_CHECK_ARG(q_row0 >= 0 && nq >= 1 && q_row0 + nq <= nk, "query rows must be a sub-range of the keys");
-    KB_CHECK_ARG(nk < (1LL << 31), "more than 2^31 keys");
-    if (impl == KB_KNN_AUTO) impl = (nk >= 512) ? KB_KNN_TC : KB_KNN_SIMT;
-    KB_CHECK_ARG(impl == KB_KNN_SIMT || impl == KB_KNN_TC, "impl");
-    KbKnnPlan p;
-    KB_CHECK_ARG(n_flag >= 0 && n_flag < (1LL << 31) && (n_flag == 0 || (d_flag_rows && d_flag_counts && ld_flag_counts >= flag_cols)),
-                 "flagged-row side inputs");
-    int rc = kb_knn_plan(ctx->sm_count, impl, nq, nk, k, n_flag, &p);
+                      void* d_workspace, int64_t workspace_bytes, const kb_knn_xchg* xchg) {
+    KbKnnEntry* ent = nullptr;
+    int rc = check_args(ctx, impl, k, d_operand, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows,
+                        d_flag_counts, ld_flag_counts, flag_cols, n_flag, d_idx, d_dist, d_workspace, workspace_bytes, &ent);
     if (rc) return rc;
-    if (p.splits * p.kp > 32 * 16) { kb_set_error("internal: too many candidates per row"); return KB_EUNSUPPORTED; }
-    if (workspace_bytes < p.total) { kb_set_error("kNN workspace: need %lld bytes, got %lld", (long long)p.total, (long long)workspace_bytes); return KB_EWORKSPACE; }
-    KB_CHECK_ARG(((uintptr_t)d_workspace % 256) == 0, "workspace must be 256-byte aligned");
+    const KbKnnPlan& p = ent->plan;
     uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
     const __half* op = reinterpret_cast<const __half*>(d_operand);
+    int32_t* uncert = reinterpret_cast<int32_t*>(ws + p.off_uncert);
 
-    k4_prep_colmeta<<<(unsigned)((p.nk_pad + 255) / 256), 256, 0, ctx->stream>>>(
-        d_rowmeta, nk, p.nk_pad, reinterpret_cast<float2*>(ws + p.off_colmeta),
-        reinterpret_cast<int32_t*>(ws + p.off_rowthr), nq);
+    k4_init<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<int32_t*>(ws + p.off_rowthr), nq, uncert,
+                                                                   p.impl == 0 ? 1 : 0);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
+    if (p.impl == 0) {
+        KB_CHECK_ARG(!xchg || xchg->n_peers == 0, "peer result stores need k <= 60");
+        return KB_OK;                                         // k > KB_KNN_K_MAX: kb_knn_fixup does all rows
+    }
+    const int32_t* slot_count = nullptr;
     {
         KbTimer t(ctx, 4);
         if (impl == KB_KNN_TC) {
-            rc = kb_knn_tc_launch(ctx, p, d_operand, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws);
+            rc = table_cached(ctx, ent);
+            if (rc) return rc;
+            const uint8_t* d = reinterpret_cast<const uint8_t*>(ent->d);
+            slot_count = reinterpret_cast<const int32_t*>(d + ent->off_slots);
+            KbTcArgs a;
+            a.d_operand = d_operand; a.ld_operand = ld_operand; a.d_cols_padded = d_cols_padded;
+            a.d_rowmeta = d_rowmeta; a.nk = nk; a.q_row0 = q_row0; a.nq = nq;
+            a.cand_score = reinterpret_cast<float*>(ws + p.off_score);
+            a.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
+            a.row_thr = reinterpret_cast<int32_t*>(ws + p.off_rowthr);
+            a.pieces = reinterpret_cast<const KbPiece*>(d);
+            a.piece_start = reinterpret_cast<const int32_t*>(d + ent->off_start);
+            a.d_arrive = xchg ? xchg->d_arrive : nullptr;
+            a.d_epoch = xchg ? xchg->d_epoch : nullptr;
+            a.rows_per_src = xchg ? xchg->rows_per_src : 0;
+            a.self_rank = xchg ? xchg->self_rank : 0;
+            rc = kb_knn_tc_launch(ctx, p, a);
         } else {
-            switch (p.kp) {
-                case 8: rc = run_simt<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
-                case 16: rc = run_simt<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
-                case 24: rc = run_simt<24>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
-                default: rc = run_simt<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws); break;
-            }
+            KB_CHECK_ARG(!xchg || !xchg->d_arrive, "the SIMT kernel does not wait for peer shards");
+#define CALL(KP) run_simt<KP>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, ws)
+            KB_KP_SWITCH(p.kp, CALL)
+#undef CALL
         }
         if (rc) return rc;
     }
     const bool extras = n_flag > 0;
     if (extras) {
         KbTimer t(ctx, 6);
-        switch (p.kp) {
-            case 8: rc = run_exact<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
-            case 16: rc = run_exact<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
-            case 24: rc = run_exact<24>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
-            default: rc = run_exact<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws); break;
-        }
+#define CALL(KP) run_exact<KP>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows, d_flag_counts, ld_flag_counts, flag_cols, (int32_t)n_flag, ws)
+        KB_KP_SWITCH(p.kp, CALL)
+#undef CALL
         if (rc) return rc;
     }
     {
         KbTimer t(ctx, 5);
-        switch (p.kp) {
-            case 8: rc = run_rerank<8>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
-            case 16: rc = run_rerank<16>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
-            case 24: rc = run_rerank<24>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
-            default: rc = run_rerank<32>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, d_idx, d_dist, d_d2); break;
-        }
+        K5Peers peers;
+        peers.n = xchg ? xchg->n_peers : 0;
+        peers.idx = xchg ? xchg->d_peer_idx : nullptr;
+        peers.dist = xchg ? xchg->d_peer_dist : nullptr;
+#define CALL(KP) run_rerank<KP>(ctx, p, op, ld_operand, d_cols_padded, d_rowmeta, q_row0, nq, k, ws, extras, slot_count, d_idx, d_dist, d_d2, peers)
+        KB_KP_SWITCH(p.kp, CALL)
+#undef CALL
     }
     return rc;
+}
+
+extern "C" int64_t kb_knn_fixup(kb_ctx* ctx, int impl, int32_t k,
+                                const void* d_operand, int64_t ld_operand, int32_t d_cols_padded,
+                                const kb_rowmeta* d_rowmeta,
+                                int64_t nk, int64_t q_row0, int64_t nq,
+                                const int32_t* d_flag_rows, const uint32_t* d_flag_counts, int64_t ld_flag_counts,
+                                int32_t flag_cols, int64_t n_flag,
+                                int32_t* d_idx, float* d_dist, double* d_d2,
+                                void* d_workspace, int64_t workspace_bytes) {
+    KbKnnEntry* ent = nullptr;
+    int rc = check_args(ctx, impl, k, d_operand, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, nq, d_flag_rows,
+                        d_flag_counts, ld_flag_counts, flag_cols, n_flag, d_idx, d_dist, d_workspace, workspace_bytes, &ent);
+    if (rc) return rc;
+    const KbKnnPlan& p = ent->plan;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
+    const int32_t* uncert = reinterpret_cast<const int32_t*>(ws + p.off_uncert);
+    int32_t n_rows = 0;
+    KB_CUDA(cudaMemcpyAsync(&n_rows, uncert, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_rows <= 0) return 0;
+    if (n_rows > nq) n_rows = (int32_t)nq;
+    const __half* op = reinterpret_cast<const __half*>(d_operand);
+    const int32_t* rows = uncert + 4;
+    // batches sized for ~1 GB of scratch: (d2 f64 + idx i32) x 2 (sort double buffers) per (row, key)
+    int64_t batch = (1LL << 30) / (nk * 24);
+    if (batch < K6_QB) batch = K6_QB;
+    batch = batch / K6_QB * K6_QB;
+    if (batch > n_rows) batch = kb_round_up(n_rows, K6_QB);
+    cudaMemPool_t pool;
+    rc = kb_pool_get(ctx, &pool);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    double *d2a = nullptr, *d2b = nullptr; int32_t *ia = nullptr, *ib = nullptr; int64_t* seg = nullptr; void* tmp = nullptr;
+    const size_t cells = (size_t)batch * (size_t)nk;
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&d2a, cells * 8, pool, st));
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&d2b, cells * 8, pool, st));
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&ia, cells * 4, pool, st));
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&ib, cells * 4, pool, st));
+    KB_CUDA(cudaMallocFromPoolAsync((void**)&seg, (size_t)(batch + 1) * 8, pool, st));
+    size_t tmp_bytes = 0;
+    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, d2a, d2b, ia, ib, (int64_t)cells, (int)batch, seg, seg + 1, 0, 64, st);
+    KB_CUDA(cudaMallocFromPoolAsync(&tmp, tmp_bytes ? tmp_bytes : 16, pool, st));
+    const size_t smem = (size_t)K6_QB * d_cols_padded * sizeof(float);
+    KB_CUDA(cudaFuncSetAttribute(k6_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KbTimer t(ctx, 6);
+        for (int64_t lo = 0; lo < n_rows; lo += batch) {
+            const int64_t nb = (n_rows - lo < batch) ? n_rows - lo : batch;
+            const int64_t q_ctas = (nb + K6_QB - 1) / K6_QB;
+            int64_t key_ctas = ((int64_t)ctx->sm_count * 8 + q_ctas - 1) / q_ctas;        // enough CTAs to fill the GPU
+            if (key_ctas > (nk + 63) / 64) key_ctas = (nk + 63) / 64;
+            if (key_ctas < 1) key_ctas = 1;
+            if (key_ctas > 65535) key_ctas = 65535;
+            const int64_t keys_per_cta = (nk + key_ctas - 1) / key_ctas;
+            k6_dist<<<dim3((unsigned)q_ctas, (unsigned)key_ctas), 256, smem, st>>>(
+                op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, rows, lo, nb, d_flag_rows, d_flag_counts,
+                ld_flag_counts, flag_cols, (int32_t)n_flag, keys_per_cta, d2a, ia);
+            ctx->launches++;
+            KB_CUDA(cudaGetLastError());
+            k6_segments<<<(unsigned)((nb + 256) / 256), 256, 0, st>>>(nk, nb, seg);
+            ctx->launches++;
+            // stable LSD radix sort on the fp64 keys: ties keep ascending key index
+            KB_CUDA(cub::DeviceSegmentedRadixSort::SortPairs(tmp, tmp_bytes, d2a, d2b, ia, ib, (int64_t)(nb * nk), (int)nb, seg, seg + 1, 0, 64, st));
+            ctx->launches += 2;
+            k6_emit<<<(unsigned)((nb * k + 255) / 256), 256, 0, st>>>(d2b, ib, nk, rows, lo, nb, k, d_idx, d_dist, d_d2);
+            ctx->launches++;
+            KB_CUDA(cudaGetLastError());
+        }
+    }
+    KB_CUDA(cudaFreeAsync(d2a, st)); KB_CUDA(cudaFreeAsync(d2b, st)); KB_CUDA(cudaFreeAsync(ia, st));
+    KB_CUDA(cudaFreeAsync(ib, st)); KB_CUDA(cudaFreeAsync(seg, st)); KB_CUDA(cudaFreeAsync(tmp, st));
+    KB_CUDA(cudaStreamSynchronize(st));
+    return n_rows;
 }

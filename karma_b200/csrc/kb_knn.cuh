@@ -2,29 +2,55 @@
 #pragma once
 #include "kb_common.cuh"
 
-// Candidate-search plan: the N x N score matrix is cut into units
-// (query block of BM rows) x (split s of the key tiles); each unit keeps a
-// running top-KP per query row and writes it to cand_*[q][s][0..KP).
-struct KbKnnPlan {
-    int impl;            // KB_KNN_SIMT / KB_KNN_TC
-    int kp;              // candidates kept per (row, split): 8 / 16 / 32
-    int bm, bn;          // unit tile shape
-    int64_t m_blocks;    // ceil(nq / bm)
-    int64_t n_tiles;     // ceil(nk / bn)
-    int splits;          // S
-    int cl;              // tensor path: CTAs per cluster sharing one key-tile stream (1, 2 or 4)
-    int64_t nk_pad;      // colmeta length (multiple of bn)
-    // workspace offsets (bytes)
-    int64_t off_colmeta, off_score, off_idx, off_rowthr, off_xidx, off_xd2, total;
+#define KB_KNN_KP_MAX 64          // widest candidate list (tensor and SIMT kernels)
+#define KB_KNN_K_MAX 60           // largest k served by the candidate kernels; beyond: exact pass over all keys
+#define KB_KNN_MAX_CAND 512       // K5 merges at most this many candidates per row (slots * KP)
+
+// One piece of work of the tensor kernel: query-block group `group` (CL adjacent 128-row blocks, one
+// per CTA of the cluster) against the key tiles tile(i), i in [i_lo, i_lo + i_cnt), of the sweep
+//     tile(i) = t_lo + ((i + shift) mod cnt)
+// (a band of `cnt` key tiles starting at t_lo, rotated so that the band holding the group's diagonal
+// starts AT the diagonal).  The running top-KP list of every row is written to candidate slot `slot`.
+struct KbPiece {
+    int32_t group, slot, t_lo, cnt, shift, i_lo, i_cnt, pad;
 };
 
-int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int32_t k, int64_t n_flag, KbKnnPlan* p);
+// Candidate-search plan.
+//  SIMT kernel: grid (m_blocks, slots); slot s covers key tiles [n_tiles*s/slots, n_tiles*(s+1)/slots).
+//  Tensor kernel: a table of pieces per worker (= CTA cluster), built on the host so that every worker
+//  gets the same number of tile visits and all workers sweep the same band of key tiles at the same time.
+struct KbKnnPlan {
+    int impl;            // KB_KNN_SIMT / KB_KNN_TC, or 0: no candidate kernel (k > KB_KNN_K_MAX: exact pass only)
+    int kp;              // candidates kept per (row, slot): 8 ... 64
+    int bm, bn;          // tile shape
+    int64_t m_blocks;    // ceil(nq / bm)
+    int64_t n_tiles;     // ceil(nk / bn)
+    int cl;              // tensor path: CTAs per cluster sharing one key-tile stream (1, 2 or 4)
+    int64_t groups;      // ceil(m_blocks / cl)
+    int workers;         // tensor path: clusters launched
+    int slots;           // candidate lists per query row (upper bound; per group see slot_count)
+    int bands;           // tensor path: S
+    int sched_kind;      // 0: whole units dealt round-robin, 1: every band cut into equal ranges
+    int64_t n_pieces;
+    double makespan;     // tile visits (+0.5 per piece) of the busiest worker
+    // workspace offsets (bytes)
+    int64_t off_score, off_idx, off_rowthr, off_xidx, off_xd2, off_uncert, total;
+};
+
+int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, int32_t dp, int32_t k, int64_t n_flag, KbKnnPlan* p);
+// tensor path: fills `pieces` (ordered by worker), `piece_start` (workers + 1) and `slot_count` (groups)
+void kb_knn_plan_pieces(const KbKnnPlan& p, int64_t q_row0, KbPiece* pieces, int32_t* piece_start, int32_t* slot_count);
 
 // score of key j for query i, up to a per-row constant and positive factor:
-//   l_i * d2_ij - n_i/l_i = l_i * n_j/l_j^2 - 2 g_ij / l_j  =  fma(g, cm.x, l_i * cm.y)
-// colmeta[j] = { -2/l_j , n_j/l_j^2 }  (+inf in .y masks a key)
+//   l_i * d2_ij - n_i/l_i = l_i * n_j/l_j^2 - 2 g_ij / l_j  =  fma(g, cm_x, l_i * cm_y)
+// kb_rowmeta carries { cm_x = -2/l_j , cm_y = n_j/l_j^2 }  (+inf in cm_y masks a key)
 __device__ __forceinline__ float kb_score(float g, float2 cm, float li) {
     return fmaf(g, cm.x, li * cm.y);
+}
+__device__ __forceinline__ float2 kb_load_cm(const kb_rowmeta* __restrict__ rowmeta, int64_t j, int64_t nk) {
+    float2 cm = make_float2(0.f, __int_as_float(0x7f800000));
+    if (j < nk) cm = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(rowmeta + j) + 16);
+    return cm;
 }
 
 // Per-row running top-KP list in shared memory, entry e of row r at [e*ROWS + r]
@@ -74,6 +100,11 @@ struct KbRowList {
     }
 };
 
-int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int64_t ld_operand,
-                     int32_t d_cols_padded, const kb_rowmeta* d_rowmeta, int64_t nk, int64_t q_row0,
-                     int64_t nq, uint8_t* ws);
+struct KbTcArgs {
+    const void* d_operand; int64_t ld_operand; int32_t d_cols_padded;
+    const kb_rowmeta* d_rowmeta; int64_t nk, q_row0, nq;
+    float* cand_score; int32_t* cand_idx; int32_t* row_thr;
+    const KbPiece* pieces; const int32_t* piece_start;
+    const uint32_t* d_arrive; const uint32_t* d_epoch; int64_t rows_per_src; int32_t self_rank;
+};
+int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const KbTcArgs& a);

@@ -16,8 +16,11 @@
 //               buffered in TMEM (2 x 256 columns)
 //   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns, one thread per query
 //               row; running top-KP list per row in shared memory
-// Work unit = (128-row query block) x (split of the key tiles); each unit writes
-// KP candidates per row, merged and exactly reranked by K5 (kb_knn.cu).
+// Work = a host-built table of pieces per cluster (kb_knn.cuh: KbPiece): a query-block group against a
+// run of key tiles; each piece writes KP candidates per row into its slot, merged and exactly reranked
+// by K5 (kb_knn.cu).  With a peer-memory exchange the TMA producer (and the epilogue, for the key
+// records) waits for the arrival flag of the rank that owns a key row before touching it, so the sweep
+// starts on the local shard while the other shards are still in flight over NVLink.
 //
 // Roofline: tensor pipe.  Algorithmic flops = 2 * nq * nk * D.
 #include "kb_knn.cuh"
@@ -135,45 +138,52 @@ __device__ unsigned long long g_tc_inserts, g_tc_cold_chunks, g_tc_chunks;
 
 struct TcParams {
     int64_t nk, q_row0, nq;
-    int64_t m_blocks, n_tiles;
-    int splits;
+    int slots;                        // candidate lists per query row (stride of cand_*)
     int k_blocks;                     // Dp / 64
-    const float2* colmeta;
     const kb_rowmeta* rowmeta;
     float* cand_score;
     int32_t* cand_idx;
-    int32_t* row_thr;                 // per query row: best known KP-th score (ordered-int key), shared by all units
+    int32_t* row_thr;                 // per query row: best known KP-th score (ordered-int key), shared by all pieces
+    const KbPiece* pieces;
+    const int32_t* piece_start;       // per cluster
+    const uint32_t* arrive;           // peer exchange (nullable): arrive[r] >= *epoch once rank r's shard has landed
+    const uint32_t* epoch;
+    int64_t rows_per_src;
+    int32_t self_rank;
 };
 
-// Work unit u -> (query block, tile sweep).  Units are ordered split-major so that the
-// CTAs running at the same time sweep the same key tiles (L2 reuse of B).  The split
-// that runs FIRST for a query block is the one holding its diagonal tile, and its sweep
-// starts at that tile: a contig's isoforms/duplicates sit next to it in the assembly,
-// so the running thresholds are near-final after one tile and (through row_thr) prune
-// every later unit of the same rows.
-struct Unit {
-    int64_t mb; int s; int64_t t_lo, cnt, shift;
-    // CL query blocks (one per CTA of the cluster) share a unit: same key tiles, same order
-    __device__ __forceinline__ Unit(const TcParams& p, int64_t u, int cl, int cta_rank) {
-        const int64_t groups = (p.m_blocks + cl - 1) / cl;
-        const int64_t grp = u % groups;
-        const int s_run = (int)(u / groups);
-        mb = grp * cl + cta_rank;
-        const int64_t td = (p.q_row0 + grp * cl * BM) / BN;           // diagonal tile of the group's first block
-        int sd = (int)((td * p.splits) / p.n_tiles);
-        while (sd + 1 < p.splits && (p.n_tiles * (sd + 1)) / p.splits <= td) ++sd;
-        while (sd > 0 && (p.n_tiles * sd) / p.splits > td) --sd;
-        s = (s_run + sd) % p.splits;
-        t_lo = (p.n_tiles * s) / p.splits;
-        cnt = (p.n_tiles * (s + 1)) / p.splits - t_lo;
-        shift = (s == sd) ? td - t_lo : 0;
+__device__ __forceinline__ KbPiece load_piece(const KbPiece* p) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p)), b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+    KbPiece pc;
+    pc.group = a.x; pc.slot = a.y; pc.t_lo = a.z; pc.cnt = a.w; pc.shift = b.x; pc.i_lo = b.y; pc.i_cnt = b.z; pc.pad = 0;
+    return pc;
+}
+__device__ __forceinline__ int64_t piece_tile(const KbPiece& pc, int i) {
+    int t = i + pc.shift;
+    if (t >= pc.cnt) t -= pc.cnt;
+    return (int64_t)pc.t_lo + t;
+}
+
+// Wait (bounded) until the shard of the rank owning key row `row` has arrived.  `seen` caches the answer.
+__device__ __forceinline__ void wait_row_arrived(const TcParams& p, uint32_t epoch, int64_t row, uint32_t& seen, int tag) {
+    if (row >= p.nk) row = p.nk - 1;
+    const int src = (int)(row / p.rows_per_src);
+    if (src == p.self_rank || ((seen >> src) & 1u)) return;
+    const uint32_t* f = p.arrive + src;
+    const long long t0 = clock64();
+    uint32_t it = 0;
+    while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        if ((++it & 0xff) == 0 && clock64() - t0 > 12000000000LL) {
+            printf("kb_knn_tc: shard of rank %d never arrived (tag %d, block %d)\n", src, tag, blockIdx.x);
+            __trap();
+        }
+        __nanosleep(64);
     }
-    __device__ __forceinline__ int64_t tile(int64_t i) const {
-        int64_t t = i + shift;
-        if (t >= cnt) t -= cnt;
-        return t_lo + t;
-    }
-};
+    seen |= 1u << src;
+}
 
 // order-preserving float <-> int key (atomicMin on signed ints)
 __device__ __forceinline__ int32_t f2key(float f) { const int32_t i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -235,18 +245,25 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
     const uint32_t tmem_base = *tmem_slot;
 
     const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
-    const int64_t n_units = ((p.m_blocks + CL - 1) / CL) * p.splits;
-    const int64_t u0 = blockIdx.x / CL, ustep = gridDim.x / CL;
+    const int worker = blockIdx.x / CL;
+    const int32_t pc_lo = p.piece_start[worker], pc_hi = p.piece_start[worker + 1];
+    const uint32_t epoch = p.arrive ? *p.epoch : 0u;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t u = u0; u < n_units; u += ustep) {
-                const Unit un(p, u, CL, cta_rank);
-                const int32_t arow = (int32_t)(p.q_row0 + un.mb * BM);
-                for (int64_t i = 0; i < un.cnt; ++i) {
-                    const int32_t brow = (int32_t)(un.tile(i) * BN);
+            uint32_t seen = 0;
+            for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
+                const KbPiece pc = load_piece(p.pieces + pi);
+                const int32_t arow = (int32_t)(p.q_row0 + ((int64_t)pc.group * CL + cta_rank) * BM);
+                for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
+                    const int32_t brow = (int32_t)(piece_tile(pc, i) * BN);
+                    if (p.arrive) {
+                        wait_row_arrived(p, epoch, brow, seen, 1);
+                        wait_row_arrived(p, epoch, (int64_t)brow + BN - 1, seen, 1);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
                         const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE_BYTES;
@@ -270,9 +287,9 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int64_t u = u0; u < n_units; u += ustep) {
-                const Unit un(p, u, CL, cta_rank);
-                for (int64_t i = 0; i < un.cnt; ++i) {
+            for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
+                const KbPiece pc = load_piece(p.pieces + pi);
+                for (int i = 0; i < pc.i_cnt; ++i) {
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -307,19 +324,21 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
         const float4* cm4 = reinterpret_cast<const float4*>(smem + L::OFF_COLMETA);
         float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t u = u0; u < n_units; u += ustep) {
-            const Unit un(p, u, CL, cta_rank);
-            const int64_t q = un.mb * BM + r;
+        uint32_t seen = 0;
+        for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
+            const KbPiece pc = load_piece(p.pieces + pi);
+            const int64_t q = ((int64_t)pc.group * CL + cta_rank) * BM + r;
             const bool live = q < p.nq;
             const float li = live ? (float)p.rowmeta[p.q_row0 + q].key_len : 1.f;
             list.init(r);
             float thr = __int_as_float(0x7f800000);          // min(own KP-th best, row_thr): the prune bound
-            for (int64_t i = 0; i < un.cnt; ++i) {
-                const int64_t n0 = un.tile(i) * BN;
-                // stage this tile's key metadata (all 128 epilogue threads); refresh the shared bound
+            for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
+                const int64_t n0 = piece_tile(pc, i) * BN;
+                // stage this tile's key records (all 128 epilogue threads); refresh the shared bound
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                cm_s[et] = p.colmeta[n0 + et];
-                cm_s[et + 128] = p.colmeta[n0 + et + 128];
+                if (p.arrive) { wait_row_arrived(p, epoch, n0 + et, seen, 5); wait_row_arrived(p, epoch, n0 + et + 128, seen, 5); }
+                cm_s[et] = kb_load_cm(p.rowmeta, n0 + et, p.nk);
+                cm_s[et + 128] = kb_load_cm(p.rowmeta, n0 + et + 128, p.nk);
                 if (live) thr = fminf(thr, key2f(__ldcg(p.row_thr + q)));
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bar_tfull + 8 * acc, acc_phase, 4);
@@ -370,7 +389,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
                 if (live && list.bound < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(list.bound));
             }
             if (live) {
-                const int64_t base = (q * p.splits + un.s) * KP;
+                const int64_t base = (q * p.slots + pc.slot) * KP;
 #pragma unroll
                 for (int e = 0; e < KP; ++e) {
                     p.cand_score[base + e] = list.s[e * BM + r];
@@ -474,18 +493,25 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t n_units = ((p.m_blocks + 1) / 2) * p.splits;
-    const int64_t u0 = blockIdx.x / 2, ustep = gridDim.x / 2;
+    const int worker = blockIdx.x / 2;
+    const int32_t pc_lo = p.piece_start[worker], pc_hi = p.piece_start[worker + 1];
+    const uint32_t epoch = p.arrive ? *p.epoch : 0u;
 
     if (warp == 0) {
         // ================= TMA producer (both CTAs) =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t u = u0; u < n_units; u += ustep) {
-                const Unit un(p, u, 2, cta_rank);
-                const int32_t arow = (int32_t)(p.q_row0 + un.mb * BM);
-                for (int64_t i = 0; i < un.cnt; ++i) {
-                    const int32_t brow = (int32_t)(un.tile(i) * BN) + 128 * cta_rank;   // my half of the key tile
+            uint32_t seen = 0;
+            for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
+                const KbPiece pc = load_piece(p.pieces + pi);
+                const int32_t arow = (int32_t)(p.q_row0 + ((int64_t)pc.group * 2 + cta_rank) * BM);
+                for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
+                    const int32_t brow = (int32_t)(piece_tile(pc, i) * BN) + 128 * cta_rank;   // my half of the key tile
+                    if (p.arrive) {
+                        wait_row_arrived(p, epoch, brow, seen, 11);
+                        wait_row_arrived(p, epoch, (int64_t)brow + 127, seen, 11);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
                         const uint32_t sa = sbase + L::OFF_STAGES + stage * STAGE2_BYTES;
@@ -503,9 +529,9 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         if (leader && lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int64_t u = u0; u < n_units; u += ustep) {
-                const Unit un(p, u, 2, 0);
-                for (int64_t i = 0; i < un.cnt; ++i) {
+            for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
+                const KbPiece pc = load_piece(p.pieces + pi);
+                for (int i = 0; i < pc.i_cnt; ++i) {
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 12);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -536,18 +562,20 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const float4* cm4 = reinterpret_cast<const float4*>(smem + L::OFF_COLMETA);
         float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t u = u0; u < n_units; u += ustep) {
-            const Unit un(p, u, 2, cta_rank);
-            const int64_t q = un.mb * BM + r;
+        uint32_t seen = 0;
+        for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
+            const KbPiece pc = load_piece(p.pieces + pi);
+            const int64_t q = ((int64_t)pc.group * 2 + cta_rank) * BM + r;
             const bool live = q < p.nq;
             const float li = live ? (float)p.rowmeta[p.q_row0 + q].key_len : 1.f;
             list.init(r);
             float thr = __int_as_float(0x7f800000);
-            for (int64_t i = 0; i < un.cnt; ++i) {
-                const int64_t n0 = un.tile(i) * BN;
+            for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
+                const int64_t n0 = piece_tile(pc, i) * BN;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                cm_s[et] = p.colmeta[n0 + et];
-                cm_s[et + 128] = p.colmeta[n0 + et + 128];
+                if (p.arrive) { wait_row_arrived(p, epoch, n0 + et, seen, 15); wait_row_arrived(p, epoch, n0 + et + 128, seen, 15); }
+                cm_s[et] = kb_load_cm(p.rowmeta, n0 + et, p.nk);
+                cm_s[et + 128] = kb_load_cm(p.rowmeta, n0 + et + 128, p.nk);
                 if (live) thr = fminf(thr, key2f(__ldcg(p.row_thr + q)));
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bar_tfull + 8 * acc, acc_phase, 14);
@@ -588,7 +616,7 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                 if (live && list.bound < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(list.bound));
             }
             if (live) {
-                const int64_t base = (q * p.splits + un.s) * KP;
+                const int64_t base = (q * p.slots + pc.slot) * KP;
 #pragma unroll
                 for (int e = 0; e < KP; ++e) {
                     p.cand_score[base + e] = list.s[e * BM + r];
@@ -611,11 +639,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <int KP, int STAGES, int CL>
-int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, const TcParams& prm) {
+int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, const TcParams& prm, int workers) {
     using L = Smem<KP, STAGES>;
     auto kern = k4_tc<KP, STAGES, CL>;
-    static int max_clusters[16] = {0};                         // per template instance and device
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set[ctx->device & 15] = true;
+    }
     cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(workers * CL));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = ctx->stream;
@@ -623,41 +656,23 @@ int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, c
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (!max_clusters[ctx->device & 15]) {
-        KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        int fit = ctx->sm_count / CL;
-        if (CL > 2) {                                          // clusters live inside one GPC: fewer than sm_count/CL may fit
-            cfg.gridDim = dim3((unsigned)(ctx->sm_count / CL * CL));
-            KB_CUDA(cudaOccupancyMaxActiveClusters(&fit, kern, &cfg));
-            if (fit < 1) { kb_set_error("kNN: no cluster of %d CTAs fits on this device", CL); return KB_ECUDA; }
-            if (fit > ctx->sm_count / CL) fit = ctx->sm_count / CL;
-        }
-        max_clusters[ctx->device & 15] = fit;
-    }
-    const int64_t n_units = ((prm.m_blocks + CL - 1) / CL) * prm.splits;
-    int64_t clusters = max_clusters[ctx->device & 15];
-    if (clusters > n_units) clusters = n_units;
-    cfg.gridDim = dim3((unsigned)(clusters * CL));
     KB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, tmap_b, prm));
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;
 }
 
-template <int KP>
-int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
-    using L = Smem2<KP, 6>;
-    auto kern = k4_tc2<KP, 6>;
+template <int KP, int STAGES>
+int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int workers) {
+    using L = Smem2<KP, STAGES>;
+    auto kern = k4_tc2<KP, STAGES>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
         KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set[ctx->device & 15] = true;
     }
-    const int64_t n_units = ((prm.m_blocks + 1) / 2) * prm.splits;
-    int64_t clusters = ctx->sm_count / 2;
-    if (clusters > n_units) clusters = n_units;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * 2));
+    cfg.gridDim = dim3((unsigned)(workers * 2));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = ctx->stream;
@@ -671,14 +686,18 @@ int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm) {
     return KB_OK;
 }
 
+// shared memory: 6 x 32 KB stages (2-CTA MMA) or 4 x 48 KB (one MMA per CTA) next to lists of up to 32 entries per
+// row; the wide lists (48, 64: n_neighbors 27..60) take the room of two stages (one for the 48 KB stages)
 template <int KP>
-int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, int cl, const TcParams& prm) {
+int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, int cl, const TcParams& prm, int workers) {
+    constexpr int ST2 = KP <= 32 ? 6 : 4;
+    constexpr int ST1 = KP <= 32 ? 4 : 3;
     // CTA pairs run one 2-CTA MMA (k4_tc2) unless KB_KNN_MMA2=0 asks for the two-MMA multicast kernel (experiments)
     const char* m2 = getenv("KB_KNN_MMA2");
-    if (cl == 2 && !(m2 && atoi(m2) == 0)) return launch_tc2<KP>(ctx, tmap, prm);
-    if (cl == 4) return launch_tc<KP, 4, 4>(ctx, tmap, tmap_b, prm);
-    if (cl == 2) return launch_tc<KP, 4, 2>(ctx, tmap, tmap_b, prm);
-    return launch_tc<KP, 4, 1>(ctx, tmap, tmap_b, prm);
+    if (cl == 2 && !(m2 && atoi(m2) == 0)) return launch_tc2<KP, ST2>(ctx, tmap, prm, workers);
+    if (cl == 4) return launch_tc<KP, ST1, 4>(ctx, tmap, tmap_b, prm, workers);
+    if (cl == 2) return launch_tc<KP, ST1, 2>(ctx, tmap, tmap_b, prm, workers);
+    return launch_tc<KP, ST1, 1>(ctx, tmap, tmap_b, prm, workers);
 }
 
 }  // namespace
@@ -693,9 +712,7 @@ extern "C" __attribute__((visibility("default"))) int kb_debug_tc_stats(unsigned
 }
 #endif
 
-int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int64_t ld_operand,
-                     int32_t d_cols_padded, const kb_rowmeta* d_rowmeta, int64_t nk, int64_t q_row0,
-                     int64_t nq, uint8_t* ws) {
+int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const KbTcArgs& a) {
     if (!ctx->encode_tiled) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -704,11 +721,11 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
         ctx->encode_tiled = fn;
     }
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)d_cols_padded, (cuuint64_t)nk};
-    const cuuint64_t gstride[1] = {(cuuint64_t)ld_operand * 2};
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.d_cols_padded, (cuuint64_t)a.nk};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.ld_operand * 2};
     const cuuint32_t box[2] = {BK, 128};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_operand),
+    CUresult cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.d_operand),
                                                     gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -717,25 +734,27 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const void* d_operand, int
     CUtensorMap tmap_b = tmap;
     if (p.cl == 4) {
         const cuuint32_t box_b[2] = {BK, (cuuint32_t)(BN / 4)};
-        cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_operand),
+        cr = ((EncodeTiledFn)ctx->encode_tiled)(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(a.d_operand),
                                                gdim, gstride, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { kb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return KB_ECUDA; }
     }
     TcParams prm;
-    prm.nk = nk; prm.q_row0 = q_row0; prm.nq = nq;
-    prm.m_blocks = p.m_blocks; prm.n_tiles = p.n_tiles; prm.splits = p.splits;
-    prm.k_blocks = d_cols_padded / BK;
-    prm.colmeta = reinterpret_cast<const float2*>(ws + p.off_colmeta);
-    prm.rowmeta = d_rowmeta;
-    prm.cand_score = reinterpret_cast<float*>(ws + p.off_score);
-    prm.cand_idx = reinterpret_cast<int32_t*>(ws + p.off_idx);
-    prm.row_thr = reinterpret_cast<int32_t*>(ws + p.off_rowthr);
+    prm.nk = a.nk; prm.q_row0 = a.q_row0; prm.nq = a.nq;
+    prm.slots = p.slots;
+    prm.k_blocks = a.d_cols_padded / BK;
+    prm.rowmeta = a.d_rowmeta;
+    prm.cand_score = a.cand_score; prm.cand_idx = a.cand_idx; prm.row_thr = a.row_thr;
+    prm.pieces = a.pieces; prm.piece_start = a.piece_start;
+    prm.arrive = a.d_arrive; prm.epoch = a.d_epoch; prm.rows_per_src = a.rows_per_src > 0 ? a.rows_per_src : 1;
+    prm.self_rank = a.self_rank;
     switch (p.kp) {
-        case 8: return launch_tc_kp<8>(ctx, tmap, tmap_b, p.cl, prm);
-        case 16: return launch_tc_kp<16>(ctx, tmap, tmap_b, p.cl, prm);
-        case 24: return launch_tc_kp<24>(ctx, tmap, tmap_b, p.cl, prm);
-        default: return launch_tc_kp<32>(ctx, tmap, tmap_b, p.cl, prm);
+        case 8: return launch_tc_kp<8>(ctx, tmap, tmap_b, p.cl, prm, p.workers);
+        case 16: return launch_tc_kp<16>(ctx, tmap, tmap_b, p.cl, prm, p.workers);
+        case 24: return launch_tc_kp<24>(ctx, tmap, tmap_b, p.cl, prm, p.workers);
+        case 32: return launch_tc_kp<32>(ctx, tmap, tmap_b, p.cl, prm, p.workers);
+        case 48: return launch_tc_kp<48>(ctx, tmap, tmap_b, p.cl, prm, p.workers);
+        default: return launch_tc_kp<64>(ctx, tmap, tmap_b, p.cl, prm, p.workers);
     }
 }

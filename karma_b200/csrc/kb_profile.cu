@@ -29,18 +29,40 @@ k2_compact(const uint32_t* __restrict__ in, int64_t ld_in, int32_t cols_in,
     }
 }
 
-// one warp per row
+// one warp per row.  Rows [n, n_alloc) are written as gather padding.  Dynamic shared memory:
+// `cols` bytes of per-CTA column presence (only when `presence` is given).
 __global__ void __launch_bounds__(256)
 k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
-             const int32_t* __restrict__ key_len, int64_t n,
+             const int32_t* __restrict__ key_len, int64_t n, int64_t n_alloc,
              double* __restrict__ profile, int64_t ld_profile,
              __half* __restrict__ operand, int64_t ld_operand,
-             kb_rowmeta* __restrict__ rowmeta) {
+             kb_rowmeta* __restrict__ rowmeta, uint32_t* __restrict__ presence, uint32_t* __restrict__ flags_or) {
+    extern __shared__ uint8_t s_pres[];
+    __shared__ int s_cnt;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int cols4 = cols & ~3;
-    for (int64_t row = warp; row < n; row += nwarps) {
+    if (presence) {
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) s_pres[c] = 0;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+    }
+    for (int64_t row = warp; row < n_alloc; row += nwarps) {
+        if (row >= n) {
+            // gather padding: zero counts, never a neighbour
+            if (operand)
+                for (int64_t c = 8 * lane; c < ld_operand; c += 256)
+                    *reinterpret_cast<uint4*>(operand + row * ld_operand + c) = make_uint4(0, 0, 0, 0);
+            if (lane == 0 && rowmeta) {
+                kb_rowmeta m;
+                m.sqnorm = 0.0; m.key_len = 1; m.flags = 11;
+                m.cm_x = 0.f; m.cm_y = __int_as_float(0x7f800000);
+                m.reserved[0] = m.reserved[1] = 0;
+                rowmeta[row] = m;
+            }
+            continue;
+        }
         const uint32_t* src = counts + row * ld;
         const double len = (double)key_len[row];
         unsigned long long sq = 0;
@@ -58,6 +80,12 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
                 sq += (unsigned long long)v.x * v.x + (unsigned long long)v.y * v.y +
                       (unsigned long long)v.z * v.z + (unsigned long long)v.w * v.w;
                 mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+                if (presence) {
+                    if (v.x) s_pres[cc] = 1;
+                    if (v.y) s_pres[cc + 1] = 1;
+                    if (v.z) s_pres[cc + 2] = 1;
+                    if (v.w) s_pres[cc + 3] = 1;
+                }
                 if (profile) {
                     double2 a, b;
                     a.x = v.x ? (double)v.x / len : 0.0;
@@ -87,6 +115,7 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
             const uint32_t v = src[c];
             sq += (unsigned long long)v * v;
             mx = max(mx, v);
+            if (presence && v) s_pres[c] = 1;
             if (profile) profile[row * ld_profile + c] = v ? (double)v / len : 0.0;
             if (operand) operand[row * ld_operand + c] = __float2half_rn((float)min(v, 2048u));
         }
@@ -97,13 +126,35 @@ k3_normalise(const uint32_t* __restrict__ counts, int64_t ld, int32_t cols,
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
         if (lane == 0) {
+            const int flags = (mx > 2048u ? 1 : 0) | (sq >= (1ull << 24) ? 2 : 0) | (mx == 0 ? 4 : 0);
             if (rowmeta) {
                 kb_rowmeta m;
                 m.sqnorm = (double)sq;
                 m.key_len = key_len[row];
-                m.flags = (mx > 2048u ? 1 : 0) | (sq >= (1ull << 24) ? 2 : 0) | (mx == 0 ? 4 : 0);
+                m.flags = flags;
+                if (flags & 3) { m.cm_x = 0.f; m.cm_y = __int_as_float(0x7f800000); }      // K4 never proposes the row
+                else { m.cm_x = (float)(-2.0 / len); m.cm_y = (float)((double)sq / (len * len)); }
+                m.reserved[0] = m.reserved[1] = 0;
                 rowmeta[row] = m;
             }
+            if (flags_or && flags) atomicOr(flags_or, (uint32_t)flags);
+        }
+    }
+    if (presence) {
+        // publish: one CTA that saw EVERY column proves the dictionary is complete with a single
+        // store; only CTAs that did not fall back to per-column stores (checked before writing:
+        // a thousand CTAs storing to the same words would cost more than the kernel)
+        __syncthreads();
+        int mine = 0;
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) mine += s_pres[c];
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
+        __syncthreads();
+        if (s_cnt == cols) {
+            if (threadIdx.x == 0 && !(__ldcg(presence + cols) & 2u)) atomicOr(presence + cols, 2u);
+        } else {
+            for (int c = threadIdx.x; c < cols; c += blockDim.x)
+                if (s_pres[c] && __ldcg(presence + c) == 0u) presence[c] = 1u;
         }
     }
 }
@@ -149,23 +200,24 @@ extern "C" int kb_compact(kb_ctx* ctx, const uint32_t* d_in, int64_t ld_in, int3
 }
 
 extern "C" int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32_t d_cols,
-                            const int32_t* d_key_len, int64_t n,
+                            const int32_t* d_key_len, int64_t n, int64_t n_alloc,
                             double* d_profile, int64_t ld_profile,
                             void* d_operand, int64_t ld_operand,
-                            kb_rowmeta* d_rowmeta) {
-    KB_CHECK_ARG(ctx && d_counts && d_key_len, "null pointer");
-    KB_CHECK_ARG(n >= 0 && d_cols > 0 && ld >= d_cols, "shape");
+                            kb_rowmeta* d_rowmeta, uint32_t* d_presence, uint32_t* d_flags_or) {
+    KB_CHECK_ARG(ctx && (n == 0 || (d_counts && d_key_len)), "null pointer");
+    KB_CHECK_ARG(n >= 0 && n_alloc >= n && d_cols > 0 && ld >= d_cols, "shape");
     KB_CHECK_ARG((ld % 4) == 0 && ((uintptr_t)d_counts % 16) == 0, "counts must be 16-byte aligned with ld % 4 == 0");
     KB_CHECK_ARG(!d_profile || (ld_profile >= d_cols && ((uintptr_t)d_profile % 16) == 0), "profile ld/alignment");
     KB_CHECK_ARG(!d_operand || (ld_operand >= d_cols && (ld_operand % 64) == 0 && ((uintptr_t)d_operand % 16) == 0),
                  "operand ld must be a multiple of 64 and >= columns");
-    if (n == 0) return KB_OK;
+    if (n_alloc == 0) return KB_OK;
     KbTimer t(ctx, 3);
-    const int64_t blocks_needed = (n + 7) / 8;
+    const int64_t blocks_needed = (n_alloc + 7) / 8;
     const int64_t grid = blocks_needed < (int64_t)ctx->sm_count * 8 ? blocks_needed : (int64_t)ctx->sm_count * 8;
-    k3_normalise<<<(unsigned)grid, 256, 0, ctx->stream>>>(d_counts, ld, d_cols, d_key_len, n, d_profile, ld_profile,
-                                                          reinterpret_cast<__half*>(d_operand), ld_operand,
-                                                          d_rowmeta);
+    const size_t smem = d_presence ? (size_t)kb_round_up(d_cols, 16) : 0;
+    k3_normalise<<<(unsigned)grid, 256, smem, ctx->stream>>>(d_counts, ld, d_cols, d_key_len, n, n_alloc, d_profile, ld_profile,
+                                                             reinterpret_cast<__half*>(d_operand), ld_operand,
+                                                             d_rowmeta, d_presence, d_flags_or);
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;

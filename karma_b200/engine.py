@@ -18,7 +18,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import KB_KNN_AUTO, KB_MODE_5P6, KB_MODE_DENSE_4_5, KB_MODE_DENSE_5_6, KB_MODE_K, check, ptr
+from ._lib import (KB_COUNT_NO_COLUMNS, KB_KNN_AUTO, KB_MODE_5P6, KB_MODE_DENSE_4_5, KB_MODE_DENSE_5_6, KB_MODE_K,
+                   check, ptr)
 
 _BASES = "ACGT"
 
@@ -247,11 +248,15 @@ class Engine:
         return d_bases, d_offsets, d_key_len, chunks
 
     # ---- K1 ----------------------------------------------------------------------
-    def count(self, d_bases, d_offsets, n, mode, counts=None, exotic=None, presence=None, zero_presence=True):
+    def count(self, d_bases, d_offsets, n, mode, counts=None, exotic=None, presence=None, zero_presence=True,
+              columns=True):
         """u32 counts (n, D) [torch.int32 storage], exotic tallies (n,), presence (D+1,):
-        presence[c] != 0 iff column c occurs, presence[D] != 0 iff a window holds a non-ACGT byte."""
+        presence[c] != 0 iff column c occurs, presence[D] bit0 iff a window holds a non-ACGT byte.
+        ``columns=False``: only presence[D] is written (K3 can derive the column words)."""
         self._bind_stream()
         cols = check(self.lib.kb_mode_columns(mode))
+        if not columns:
+            mode = mode | KB_COUNT_NO_COLUMNS
         if counts is None:
             counts = torch.empty((n, cols), dtype=torch.int32, device=self.device)
         if exotic is None:
@@ -319,10 +324,11 @@ class Engine:
 
     # ---- K3 ------------------------------------------------------------------------
     def normalise(self, counts, d_cols, d_key_len, want_profile=True, want_operand=True, profile=None,
-                  rows_alloc=None, launch=True):
+                  rows_alloc=None, launch=True, presence=None, flags_or=None):
         """K3.  With ``rows_alloc`` > n the kNN inputs are allocated with that many rows
-        (the equal-size shard a rank contributes to the all-gather); the padding rows are
-        zero counts, key_len 1 and flagged so that they can never be neighbours."""
+        (the equal-size shard a rank contributes to the exchange); K3 writes the padding rows
+        (zero counts, flagged so that they can never be neighbours).  ``presence`` (D+1 words,
+        accumulating) / ``flags_or`` (1 word, accumulating) as in kb_normalise."""
         self._bind_stream()
         n = counts.shape[0]
         rows = n if rows_alloc is None else max(n, int(rows_alloc))
@@ -331,49 +337,82 @@ class Engine:
             profile = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
         dp = (d_cols + 63) // 64 * 64
         operand = torch.empty((rows, dp), dtype=torch.float16, device=self.device) if want_operand else None
-        # kb_rowmeta records (16 B): [sqnorm f64 | key_len i32 | flags i32] viewed as int32 x 4
-        rowmeta = torch.empty((rows, 4), dtype=torch.int32, device=self.device)
-        if rows > n:
-            if operand is not None:
-                operand[n:] = 0
-            rowmeta[n:] = torch.tensor([0, 0, 1, 11], dtype=torch.int32, device=self.device)   # flags 1|2|8: padding
+        # kb_rowmeta records (32 B): [sqnorm f64 | key_len i32 | flags i32 | cm_x f32 | cm_y f32 | 2 x reserved]
+        rowmeta = torch.empty((rows, 8), dtype=torch.int32, device=self.device)
         if launch:
-            self.normalise_rows(counts, d_cols, d_key_len, 0, n, profile, operand, rowmeta)
+            self.normalise_rows(counts, d_cols, d_key_len, 0, n, profile, operand, rowmeta, rows, presence, flags_or)
         return profile, operand, rowmeta
 
-    def normalise_rows(self, counts, d_cols, d_key_len, lo, hi, profile, operand, rowmeta):
-        """K3 on rows [lo, hi) of preallocated outputs (the chunked upload path runs it per chunk)."""
+    def normalise_rows(self, counts, d_cols, d_key_len, lo, hi, profile, operand, rowmeta, rows_alloc=None,
+                       presence=None, flags_or=None):
+        """K3 on rows [lo, hi) of preallocated outputs (the chunked upload path runs it per chunk);
+        ``rows_alloc``: total rows of operand/rowmeta -- the call that reaches the last real row also writes
+        the padding rows behind it."""
         self._bind_stream()
-        if hi <= lo:
+        n = counts.shape[0]
+        n_alloc = hi - lo
+        if rows_alloc is not None and hi == n:
+            n_alloc = int(rows_alloc) - lo
+        if n_alloc <= 0:
             return
-        c = counts[lo:hi]
-        check(self.lib.kb_normalise(self.ctx, ptr(c), counts.stride(0), d_cols, ptr(d_key_len[lo:hi]), hi - lo,
-                                    ptr(profile[lo:hi]) if profile is not None else None,
+        c = counts[lo:hi] if hi > lo else counts[0:0]
+        check(self.lib.kb_normalise(self.ctx, ptr(c) if hi > lo else None, counts.stride(0), d_cols,
+                                    ptr(d_key_len[lo:hi]) if hi > lo else None, hi - lo, n_alloc,
+                                    ptr(profile[lo:hi]) if profile is not None and hi > lo else None,
                                     profile.stride(0) if profile is not None else 0,
-                                    ptr(operand[lo:hi]) if operand is not None else None,
-                                    operand.stride(0) if operand is not None else 0, ptr(rowmeta[lo:hi])))
+                                    ptr(operand[lo:]) if operand is not None else None,
+                                    operand.stride(0) if operand is not None else 0, ptr(rowmeta[lo:]),
+                                    ptr(presence), ptr(flags_or)))
 
     # ---- K4 + K5 ---------------------------------------------------------------------
-    def knn(self, operand, rowmeta, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False,
-            flag_rows=None, flag_counts=None):
-        """K4 (+K4x) + K5.  flag_rows (int32, ascending key rows) / flag_counts (u32 rows, same
-        order) describe the rows the tensor path cannot score exactly (kb_rowmeta flags 1|2)."""
+    def knn_enqueue(self, operand, rowmeta, k, q_row0=0, nq=None, impl=KB_KNN_AUTO, want_d2=False,
+                    flag_rows=None, flag_counts=None, out=None, xchg=None):
+        """Enqueue K4 (+K4x) + K5.  Returns (idx, dist, d2, fixup): ``fixup()`` synchronises, redoes the rows
+        K5 could not certify with exact distances to all keys (kb_knn_fixup) and returns how many there were.
+        flag_rows (int32, ascending key rows) / flag_counts (u32 rows, same order) describe the rows the
+        tensor path cannot score exactly (kb_rowmeta flags 1|2).  ``out``: preallocated (idx, dist)."""
         self._bind_stream()
         nk, dp = operand.shape
         nq = nk - q_row0 if nq is None else nq
         n_flag = 0 if flag_rows is None else int(flag_rows.numel())
-        need = check(self.lib.kb_knn_workspace_bytes(nq, nk, k, impl, n_flag))
+        need = check(self.lib.kb_knn_workspace_bytes(self.ctx, nq, nk, q_row0, dp, k, impl, n_flag))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
-        dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        ws = self._ws
+        if out is None:
+            idx = torch.empty((nq, k), dtype=torch.int32, device=self.device)
+            dist = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        else:
+            idx, dist = out
         d2 = torch.empty((nq, k), dtype=torch.float64, device=self.device) if want_d2 else None
-        check(self.lib.kb_knn(self.ctx, impl, k, ptr(operand), operand.stride(0), dp, ptr(rowmeta),
-                              nk, q_row0, nq,
-                              ptr(flag_rows) if n_flag else None, ptr(flag_counts) if n_flag else None,
-                              flag_counts.stride(0) if n_flag else 0, flag_counts.shape[1] if n_flag else 0, n_flag,
-                              ptr(idx), ptr(dist), ptr(d2), ptr(self._ws), self._ws.numel()))
+        args = (self.ctx, impl, k, ptr(operand), operand.stride(0), dp, ptr(rowmeta), nk, q_row0, nq,
+                ptr(flag_rows) if n_flag else None, ptr(flag_counts) if n_flag else None,
+                flag_counts.stride(0) if n_flag else 0, flag_counts.shape[1] if n_flag else 0, n_flag,
+                ptr(idx), ptr(dist), ptr(d2), ptr(ws), ws.numel())
+        check(self.lib.kb_knn(*args, xchg))
+
+        def fixup():
+            self._bind_stream()
+            return check(self.lib.kb_knn_fixup(*args))
+        return idx, dist, d2, fixup
+
+    def knn(self, operand, rowmeta, k, **kw):
+        """K4 (+K4x) + K5 + the exact pass over rows that could not be certified.  Synchronises."""
+        idx, dist, d2, fixup = self.knn_enqueue(operand, rowmeta, k, **kw)
+        self.last_uncertified = fixup()
         return idx, dist, d2
+
+    def word_view(self, addr):
+        """1-element int32 tensor aliasing a device word inside the kNN workspace."""
+        off = addr - self._ws.data_ptr()
+        assert 0 <= off < self._ws.numel() and off % 4 == 0
+        return self._ws[off:off + 4].view(torch.int32)
+
+    def uncertified_word(self, nq, nk, q_row0, dp, k, impl, n_flag=0):
+        """Device address (int) of the word in which the last knn_enqueue of this shape counts its uncertified rows."""
+        out = c_void_p()
+        check(self.lib.kb_knn_uncertified_ptr(self.ctx, nq, nk, q_row0, dp, k, impl, n_flag, ptr(self._ws), byref(out)))
+        return out.value
 
 
 # ---------------------------------------------------------------------------------------
@@ -400,110 +439,118 @@ def device_pass(engine, *args, **kwargs):
         engine._hold_stream = held
 
 
+def _presence_summary(pres, faithful):
+    """(exotic_seen, all_columns_present) from a presence vector: [D] bit0 = a non-ACGT byte was seen,
+    bit1 = some CTA of K3 saw every column (then the per-column words were not written)."""
+    last = int(pres[-1])
+    return bool(last & 1), bool(last & 2) or bool(np.asarray(pres[:-1]).all())
+
+
 def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_neighbors=None, impl=KB_KNN_AUTO,
                  want_profile=True, group=None, rank=0, world=1, n_total=None, gather_lists=False, bufs=None,
                  on_profile=None, optimistic=True, row0=0, chunks=None):
     """The hot path on device-resident inputs: K1 -> column dictionary (-> K1x/K2) -> K3
-    [-> all-gather of the operand shards -> K4 (-> K4x) -> K5].  Returns device tensors plus
-    the column list.
+    [-> all-gather of the operand shards -> K4 (-> K4x) -> K5 (-> K6)].  Returns device tensors plus
+    the column list.  This is the eager, general form (any input); `PassPlan` is the pre-planned,
+    graph-captured form of its optimistic branch for repeated passes.
 
     ``optimistic``: real assemblies contain every ACGT k-mer column, no non-ACGT bytes and no
     row beyond the exact range of the tensor path, so the whole pass is enqueued without a
-    host round trip on that assumption; the presence vector and the row records are copied
-    back asynchronously and VALIDATED at the end (one synchronisation per pass).  If the
-    assumption fails the pass is redone on the general path (compaction, exotic keys, exact
-    side path).  ``bufs``: optional preallocated counts/exotic/presence tensors.
-    ``on_profile(profile, lo, hi)`` is called as soon as K3 of rows [lo, hi) has been enqueued
-    (to start their D2H).  ``chunks`` = [(row_lo, row_hi, event)] from upload_chunked: the
-    optimistic pass then counts/normalises chunk by chunk as the uploads land."""
+    host round trip on that assumption; a few validation words are copied back asynchronously and
+    checked at the end (one synchronisation per pass).  If the assumption fails the pass is redone on
+    the general path (compaction, exotic keys, exact side path).  ``bufs``: optional preallocated
+    counts/exotic/presence tensors.  ``on_profile(profile, lo, hi)`` is called as soon as K3 of rows
+    [lo, hi) has been enqueued (to start their D2H).  ``chunks`` = [(row_lo, row_hi, event)] from
+    upload_chunked: the optimistic pass then counts/normalises chunk by chunk as the uploads land."""
     mode = mode_of(kmer_size)
     b = bufs or {}
     faithful = mode == KB_MODE_5P6 or mode >= 16
     names = mode_column_names(mode)
     main = torch.cuda.current_stream(engine.device)
     multi = group is not None and world > 1
+    cols_full = len(names)
+    per = shard_bounds(n_total, world, rank)[2] if multi else None
+    want_knn = n_neighbors is not None
     if chunks and not optimistic:
         for _, _, ev in chunks:
             main.wait_event(ev)
         chunks = None
-    if chunks:
-        cols_full = len(names)
-        counts = b.get("counts") if b.get("counts") is not None else torch.empty((n, cols_full), dtype=torch.int32, device=engine.device)
-        exotic = b.get("exotic") if b.get("exotic") is not None else torch.empty(n, dtype=torch.int32, device=engine.device)
-        presence = b.get("presence") if b.get("presence") is not None else torch.empty(cols_full + 1, dtype=torch.int32, device=engine.device)
-        presence.zero_()
-        per = shard_bounds(n_total, world, rank)[2] if multi else None
-        profile, operand, rowmeta = engine.normalise(counts, cols_full, d_key_len, want_profile=want_profile,
-                                                     want_operand=n_neighbors is not None, rows_alloc=per, launch=False)
-        for lo, hi, ev in chunks:
-            main.wait_event(ev)
-            if hi > lo:
-                engine.count(d_bases, d_offsets[lo:], hi - lo, mode, counts[lo:hi], exotic[lo:hi], presence, zero_presence=False)
-                engine.normalise_rows(counts, cols_full, d_key_len, lo, hi, profile, operand, rowmeta)
-                if on_profile is not None and profile is not None:
-                    on_profile(profile, lo, hi)
-    else:
-        counts, exotic, presence = engine.count(d_bases, d_offsets, n, mode, b.get("counts"), b.get("exotic"), b.get("presence"))
-    # every rank must agree on the column dictionary: MAX over the presence vectors.  On the optimistic
-    # path that only feeds the end-of-pass validation, so the vectors ride along with the k-list gather
-    # instead of paying for a collective of their own.
-    fold_presence = multi and optimistic and gather_lists and n_neighbors is not None
-    if multi and not fold_presence:
-        import torch.distributed as dist
-        dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)     # one D+1 word collective
+    counts = b.get("counts") if b.get("counts") is not None else torch.empty((n, cols_full), dtype=torch.int32, device=engine.device)
+    exotic = b.get("exotic") if b.get("exotic") is not None else torch.empty(n, dtype=torch.int32, device=engine.device)
+    presence = b.get("presence") if b.get("presence") is not None else torch.empty(cols_full + 1, dtype=torch.int32, device=engine.device)
+    presence.zero_()
+    d_or = torch.zeros(1, dtype=torch.int32, device=engine.device)
+    profile = operand = rowmeta = None
     if optimistic:
+        # K1 leaves the column words to K3, which reads every row anyway
+        profile, operand, rowmeta = engine.normalise(counts, cols_full, d_key_len, want_profile=want_profile,
+                                                     want_operand=want_knn, rows_alloc=per, launch=False)
+        for lo, hi, ev in (chunks or [(0, n, None)]):
+            if ev is not None:
+                main.wait_event(ev)
+            if hi > lo:
+                engine.count(d_bases, d_offsets[lo:], hi - lo, mode, counts[lo:hi], exotic[lo:hi], presence,
+                             zero_presence=False, columns=False)
+            if hi > lo or hi == n:
+                engine.normalise_rows(counts, cols_full, d_key_len, lo, hi, profile, operand, rowmeta,
+                                      rows_alloc=rowmeta.shape[0], presence=presence, flags_or=d_or)
+            if hi > lo and on_profile is not None and profile is not None:
+                on_profile(profile, lo, hi)
         columns = names
-    elif faithful:
-        columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence,
-                                               group=group if multi else None, reduced=True)
     else:
-        if int(presence[-1].item()):
-            raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (some windows contain other bytes)")
-        columns = names
+        engine.count(d_bases, d_offsets, n, mode, counts, exotic, presence, zero_presence=False)
+        if multi:
+            import torch.distributed as dist
+            dist.all_reduce(presence, op=dist.ReduceOp.MAX, group=group)     # one D+1 word collective
+        if faithful:
+            columns, counts = engine.build_columns(mode, d_bases, d_offsets, n, counts, exotic, presence,
+                                                   group=group if multi else None, reduced=True)
+        else:
+            if int(presence[-1].item()) & 1:
+                raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (some windows contain other bytes)")
+            columns = names
     d_cols = len(columns)
     if d_cols == 0:
         raise ZeroRowError(row0)
-    if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
-        counts = counts.contiguous()
-    per = shard_bounds(n_total, world, rank)[2] if multi else None
-    if not chunks:
-        profile, operand, rowmeta = engine.normalise(
-            counts, d_cols, d_key_len, want_profile=want_profile, want_operand=n_neighbors is not None, rows_alloc=per)
+    if not optimistic:
+        if counts.stride(0) % 4 != 0 or counts.data_ptr() % 16 != 0:
+            counts = counts.contiguous()
+        profile, operand, rowmeta = engine.normalise(counts, d_cols, d_key_len, want_profile=want_profile,
+                                                     want_operand=want_knn, rows_alloc=per, flags_or=d_or)
         if on_profile is not None and profile is not None:
             on_profile(profile, 0, n)
     out = {"columns": columns, "d_cols": d_cols, "counts": counts, "profile": profile, "operand": operand,
            "rowmeta": rowmeta, "idx": None, "dist": None}
     all_op, all_meta = operand, rowmeta
-    if n_neighbors is not None and multi:
-        # the one exchange step: every rank needs all keys -- two collectives, the fp16
-        # operand shards and the 16-byte row records
+    if want_knn and multi:
+        # the one exchange step: every rank needs all keys -- the fp16 operand shards and the 32-byte row records
         all_op = all_gather_rows(operand, group)
         all_meta = all_gather_rows(rowmeta, group)
+        check(engine.lib.kb_rowmeta_flags_or(engine.ctx, ptr(all_meta), all_meta.shape[0], ptr(d_or)))   # every rank's flags
     n_real = n_total if multi else n                    # padded index == global row: real rows are [0, n_real)
-    # one word summarises every row record (OR of the flags): that is all the host reads back
-    d_or = torch.empty(1, dtype=torch.int32, device=engine.device)
-    check(engine.lib.kb_rowmeta_flags_or(engine.ctx, ptr(all_meta), all_meta.shape[0], ptr(d_or)))
-    h_or = engine.host_buffer("flags_or", (1,), torch.int32, True)
-    h_pres = engine.host_buffer("presence", (len(names) + 1,), torch.int32, True)
+    h_val = engine.host_buffer("validation", (cols_full + 4,), torch.int32, True)   # [0] flags OR, [1] uncertified rows, [3..] presence
+    d_unc = None
 
     def fetch_validation_words():
         # Small D2H copies are issued only where the stream has nothing left to launch behind
         # them: a copy queued between K3 and K4 would sit behind the 0.4 GB profile transfer on
         # the D2H copy engine and stall the kNN kernels of this stream.
-        h_or.copy_(d_or, non_blocking=True)
-        h_pres.copy_(presence, non_blocking=True)
+        h_val[0:1].copy_(d_or, non_blocking=True)
+        if d_unc is not None:
+            h_val[1:2].copy_(d_unc, non_blocking=True)
+        h_val[3:].copy_(presence, non_blocking=True)
         torch.cuda.current_stream(engine.device).synchronize()
 
     def flags_host():
         """Per-row flags (general path only: the optimistic path reads just the OR word)."""
         return all_meta[:n_real, 3].cpu().numpy()
 
-    if n_neighbors is not None:
+    if want_knn:
         flag_rows = flag_counts = None
         ids = []
         if not optimistic:
             fetch_validation_words()
-            if int(h_or.numpy()[0]) & 3:                 # some row is beyond the exact range of the tensor path
+            if int(h_val.numpy()[0]) & 3:                 # some row is beyond the exact range of the tensor path
                 ids = np.flatnonzero((flags_host() & 3) != 0).astype(np.int32)
             if len(ids):
                 # true u32 count rows of the flagged contigs, in ascending global order
@@ -512,7 +559,6 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
                 local = counts[torch.from_numpy(mine.astype(np.int64)).to(engine.device)][:, :d_cols].contiguous() \
                     if len(mine) else torch.zeros((0, d_cols), dtype=torch.int32, device=engine.device)
                 if multi:
-                    import torch.distributed as dist
                     fmax = max(int(((ids >= r * per) & (ids < (r + 1) * per)).sum()) for r in range(world))
                     pad = torch.zeros((fmax, d_cols), dtype=torch.int32, device=engine.device)
                     pad[:len(mine)] = local
@@ -523,39 +569,61 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
                 else:
                     flag_counts = local
                 flag_rows = torch.from_numpy(ids).to(engine.device)
-        idx, dst, _ = engine.knn(all_op, all_meta, n_neighbors, q_row0=(rank * per if multi else 0), nq=n, impl=impl,
-                                 flag_rows=flag_rows, flag_counts=flag_counts)
-        if multi and gather_lists:
-            # k-lists back to every rank: [idx | dist bits] packed per row, one collective
+        q_row0 = rank * per if multi else 0
+        idx, dst, _, fixup = engine.knn_enqueue(all_op, all_meta, n_neighbors, q_row0=q_row0, nq=n, impl=impl,
+                                                flag_rows=flag_rows, flag_counts=flag_counts)
+        impl_used = impl if impl != KB_KNN_AUTO else (_lib.KB_KNN_TC if all_op.shape[0] >= 512 else _lib.KB_KNN_SIMT)
+        unc_addr = engine.uncertified_word(n, all_op.shape[0], q_row0, all_op.shape[1], n_neighbors, impl_used,
+                                           0 if flag_rows is None else int(flag_rows.numel()))
+        d_unc = engine.word_view(unc_addr)
+
+        def gather_all_lists():
+            # k-lists back to every rank: [idx | dist bits] packed per row, plus one row-block that carries
+            # the validation words (presence, flags, uncertified rows) -- one collective
             w2 = 2 * n_neighbors
-            extra = -(-(len(names) + 1) // w2) if fold_presence else 0      # rows that carry the presence words
+            nwords = cols_full + 3
+            extra = -(-nwords // w2)
             packed = torch.empty((per + extra, w2), dtype=torch.int32, device=engine.device)
             if per > n:
                 packed[n:per] = -1
             packed[:n, :n_neighbors] = idx
             packed[:n, n_neighbors:] = dst.view(torch.int32)
-            if extra:
-                packed[per:].view(-1)[:len(names) + 1] = presence
+            tail = packed[per:].view(-1)
+            tail[:cols_full + 1] = presence
+            tail[cols_full + 1:cols_full + 2] = d_or
+            tail[cols_full + 2:cols_full + 3] = d_unc
             g = all_gather_rows(packed, group).view(world, per + extra, w2)
             lists = g[:, :per].reshape(world * per, w2)
             out.update(all_idx=lists[:, :n_neighbors], all_dist=lists[:, n_neighbors:].view(torch.float32))
-            if extra:
-                presence = g[:, per:].reshape(world, -1)[:, :len(names) + 1].max(dim=0).values.contiguous()
+            return g[:, per:].reshape(world, -1)[:, :nwords]
+
+        if multi and gather_lists:
+            words = gather_all_lists()                               # (world, D+3)
+            presence = words[:, :cols_full + 1].max(dim=0).values.contiguous()
+            d_or = words[:, cols_full + 1].max().reshape(1).contiguous() | d_or
+            d_unc = words[:, cols_full + 2].max().reshape(1).contiguous()
         out.update(idx=idx, dist=dst)
 
     # ---- validation (the only host synchronisation of an optimistic pass)
     fetch_validation_words()
-    flags_or = int(h_or.numpy()[0])
+    hv = h_val.numpy()
+    flags_or = int(hv[0])
+    if want_knn and int(hv[1]) > 0 and not (optimistic and (flags_or & 3)):
+        # some row could not be certified from its candidate list: exact pass over all keys for those rows
+        # (every rank takes part when the lists are shared, so that the re-gather below stays collective)
+        out["uncertified"] = int(fixup())
+        if multi and gather_lists:
+            gather_all_lists()
     if optimistic:
-        pres = h_pres.numpy()
+        exo, complete = _presence_summary(hv[3:], faithful)
         redo = False
-        if pres[-1] != 0:
+        if exo:
             if not faithful:
                 raise _lib.KarmaB200Error(-4, "dense column modes accept A/C/G/T only (some windows contain other bytes)")
             redo = True
-        if faithful and not pres[:-1].all():
+        if faithful and not complete:
             redo = True
-        if n_neighbors is not None and (flags_or & 3):
+        if want_knn and (flags_or & 3):
             redo = True
         if redo:
             return _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size, n_neighbors, impl, want_profile,
@@ -616,7 +684,7 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
                     want_profile=want_profile, group=group, rank=rank, world=world, n_total=n_total,
                     on_profile=start_download if want_profile else None, row0=row0, chunks=chunks)
     out = {"columns": r["columns"], "profile": None, "knn_idx": None, "knn_dist": None,
-           "d_profile": r["profile"], "d_operand": r["operand"]}
+           "d_profile": r["profile"], "d_operand": r["operand"], "uncertified": r.get("uncertified", 0)}
     if n_neighbors is not None:
         h_idx = engine.host_buffer("knn_idx", tuple(r["idx"].shape), torch.int32, reuse_host)
         h_dst = engine.host_buffer("knn_dist", tuple(r["dist"].shape), torch.float32, reuse_host)

@@ -59,9 +59,9 @@ def test_pure_host_entry_points(lib):
     assert lib.kb_mode_columns(_lib.KB_MODE_DENSE_4_5) == 1280
     assert [lib.kb_mode_columns(_lib.KB_MODE_K(k)) for k in range(1, 8)] == [4 ** k for k in range(1, 8)]
     assert lib.kb_mode_columns(999) < 0 and b"unknown column mode" in lib.kb_last_error()
-    assert lib.kb_knn_workspace_bytes(1000, 1000, 2, 0, 0) > 0
-    assert lib.kb_knn_workspace_bytes(1000, 1000, 200, 0, 0) < 0          # unsupported k is an error, not a fallback
-    assert lib.kb_knn_workspace_bytes(10, 5, 8, 0, 0) < 0                  # k > nk
+    assert lib.kb_knn_workspace_bytes(None, 1000, 1000, 0, 1088, 2, 0, 0) > 0
+    assert lib.kb_knn_workspace_bytes(None, 1000, 1000, 0, 1088, 200, 0, 0) > 0   # any n_neighbors <= keys (cmd_parser.py:101-107): exact pass
+    assert lib.kb_knn_workspace_bytes(None, 10, 5, 0, 1088, 8, 0, 0) < 0          # k > nk
 
 
 def test_no_cpu_fallback(lib):
@@ -115,21 +115,69 @@ def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
 
 def test_knn_plan_workspace_bounds(lib, monkeypatch):
     """kb_knn_workspace_bytes (host only) over the shapes of BASELINE.json and the shard shapes of 2-8 GPUs:
-    the plan never asks for more candidate slots than K5 can merge (512 per row) and always covers the
-    per-key metadata, for every cluster variant."""
+    the plan never asks for more candidate slots than K5 can merge (512 per row), for every cluster variant."""
     from karma_b200 import _lib
-    shapes = [(1000, 1000), (50000, 50000), (6250, 50000), (62500, 500000), (125000, 1000000), (250000, 2000000), (130, 130), (513, 513)]
+    shapes = [(1000, 1000, 0), (50000, 50000, 0), (6250, 50000, 18750), (62500, 500000, 62500), (125000, 1000000, 0),
+              (250000, 2000000, 1750000), (130, 130, 0), (513, 513, 0)]
     for cluster in (None, "1", "2", "4"):
         if cluster is None:
             monkeypatch.delenv("KB_KNN_CLUSTER", raising=False)
         else:
             monkeypatch.setenv("KB_KNN_CLUSTER", cluster)
-        for nq, nk in shapes:
-            for k in (2, 10, 15, 24):
-                kp = 8 if k <= 2 else 16 if k <= 10 else 24 if k <= 18 else 32
-                for impl in (_lib.KB_KNN_SIMT, _lib.KB_KNN_TC):
-                    b = lib.kb_knn_workspace_bytes(nq, nk, k, impl, 0)
-                    lo = nk * 8 + nq * kp * 8 + nq * 4                       # colmeta + one split of candidates + row bounds
-                    hi = (nk + 256) * 8 + nq * 512 * 8 + nq * 4 + 8 * 256    # at most 512 candidates per row
-                    assert lo <= b <= hi, (cluster, nq, nk, k, impl, b, lo, hi)
-                    assert lib.kb_knn_workspace_bytes(nq, nk, k, impl, 7) > b    # flagged rows add the fp64 side lists
+        for nq, nk, q0 in shapes:
+            for dp in (1088, 5120):
+                for k in (2, 10, 15, 24, 40, 60):
+                    kp = 8 if k <= 2 else 16 if k <= 10 else 24 if k <= 18 else 32 if k <= 26 else 48 if k <= 42 else 64
+                    for impl in (_lib.KB_KNN_SIMT, _lib.KB_KNN_TC):
+                        b = lib.kb_knn_workspace_bytes(None, nq, nk, q0, dp, k, impl, 0)
+                        lo = nq * kp * 8 + nq * 4 + nq * 4                       # one list of candidates + row bounds + uncertified rows
+                        hi = nq * 512 * 8 + nq * 8 + 8 * 256                     # at most 512 candidates per row
+                        assert lo <= b <= hi, (cluster, nq, nk, k, impl, b, lo, hi)
+                        assert lib.kb_knn_workspace_bytes(None, nq, nk, q0, dp, k, impl, 7) > b    # flagged rows add the fp64 side lists
+
+
+def _plan(lib, nq, nk, q0, dp, k, sm=148):
+    import numpy as np
+    out = (ctypes.c_int64 * 8)()
+    assert lib.kb_knn_plan_info(sm, 2, nq, nk, q0, dp, k, out) == 0, lib.kb_last_error()
+    info = dict(zip(("kp", "slots", "bands", "kind", "workers", "pieces", "makespan", "ideal"), list(out)))
+    pieces = np.zeros((info["pieces"], 8), dtype=np.int32)
+    start = np.zeros(info["workers"] + 1, dtype=np.int32)
+    m_blocks = -(-nq // 128)
+    cl = 2 if m_blocks >= 2 else 1
+    groups = -(-m_blocks // cl)
+    slots = np.zeros(groups, dtype=np.int32)
+    vp = ctypes.c_void_p
+    assert lib.kb_knn_plan_table(sm, 2, nq, nk, q0, dp, k, pieces.ctypes.data_as(vp), start.ctypes.data_as(vp),
+                                 slots.ctypes.data_as(vp)) == 0
+    return info, pieces, start, slots, groups
+
+
+@pytest.mark.parametrize("nq,nk,q0,dp,k", [(50000, 50000, 0, 1088, 2), (6250, 50000, 18750, 1088, 2), (6250, 50000, 43750, 1088, 15),
+                                           (12500, 50000, 12500, 1088, 2), (25000, 50000, 25000, 1088, 2), (50000, 50000, 0, 5120, 15),
+                                           (62500, 500000, 62500, 5120, 15), (700, 700, 0, 1088, 60), (130, 130, 0, 1088, 24),
+                                           (257, 700, 300, 1088, 5), (1, 600, 599, 64, 1)])
+def test_knn_piece_table_covers_every_tile_once(lib, nq, nk, q0, dp, k):
+    """The host-built schedule of the tensor kernel (kb_knn.cuh: KbPiece): every (query group, key tile) pair is
+    visited exactly once, every piece has a candidate slot of its own, and the busiest cluster carries at most
+    a few tile visits more than the mean (small shards must keep all 74 CTA pairs busy)."""
+    import numpy as np
+    info, pieces, start, slots, groups = _plan(lib, nq, nk, q0, dp, k)
+    n_tiles = -(-nk // 256)
+    cover = np.zeros((groups, n_tiles), dtype=np.int32)
+    seen = set()
+    for g, slot, t_lo, cnt, shift, i_lo, i_cnt, _ in pieces:
+        assert (g, slot) not in seen and 0 <= slot < slots[g] <= info["slots"]
+        seen.add((g, slot))
+        assert 0 <= i_lo and i_lo + i_cnt <= cnt and i_cnt >= 1 and 0 <= shift < cnt
+        i = np.arange(i_lo, i_lo + i_cnt) + shift
+        cover[g, np.where(i >= cnt, i - cnt, i) + t_lo] += 1
+    assert (cover == 1).all()
+    assert info["slots"] * info["kp"] <= 512
+    assert start[0] == 0 and start[-1] == len(pieces) and (np.diff(start) >= 0).all()
+    loads = np.array([pieces[start[w]:start[w + 1], 6].sum() for w in range(info["workers"])])
+    mean = groups * n_tiles / info["workers"]
+    assert loads.max() <= mean * 1.04 + 2 * info["bands"], (loads.max(), mean, info)
+    if nk * dp * 2 > 120e6 and n_tiles >= 2:
+        # a key set beyond the L2 is swept in whole bands, dealt round-robin, so that concurrent clusters share key tiles
+        assert info["kind"] == 0 and info["bands"] >= 2 and (pieces[:, 5] == 0).all() and (pieces[:, 6] == pieces[:, 3]).all()

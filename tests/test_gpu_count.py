@@ -71,7 +71,7 @@ def test_long_contig_split_path(engine, mode):
     n_long, ex_total = engine.count_stats()
     want, wexo = ko.counts_mode(bases, offsets, mode)
     L = np.array(lens)
-    assert n_long in (int((L > 65536).sum()), int((L > 4096).sum())) and n_long >= 4   # small inputs use the 4 kb policy
+    assert n_long in (int((L > 65536).sum()), int((L > 16384).sum())) and n_long >= 4   # CTA-per-contig modes split above 16 kb when contigs are few
     assert np.array_equal(got, want)
     assert np.array_equal(exotic, wexo.astype(np.uint32)) and ex_total == int(wexo.sum())
     assert np.array_equal(presence, want.any(0))

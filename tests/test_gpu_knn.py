@@ -159,3 +159,125 @@ def test_dense_5120_k15_at_scale(engine):
     rows = np.arange(0, 12000, 401)
     rep = knn_oracle.check_knn(idx[rows], dist[rows], knn_oracle.d2_fp64(res["profile"], rows), rows=rows)
     assert knn_oracle.parity_ok(rep), rep
+
+
+# ---------------------------------------------------------------------------------------------
+# wide candidate lists, any n_neighbors, and the certificate behind the candidate width
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("k", [27, 42, 60])
+def test_knn_parity_wide_lists(engine, impl, k):
+    """n_neighbors 27..60: candidate lists of 48 / 64 entries per row (cmd_parser.py:101-107 accepts any int)."""
+    asm = synth.s1_families(700, seed=5)
+    res = _run(engine, asm, "5p6", k, impl)
+    cols, prof = ko.profile_np(asm.as_dict(), "5p6")
+    assert res["profile"].tobytes() == prof.tobytes()
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+
+
+@pytest.mark.parametrize("k", [61, 150])
+def test_knn_any_n_neighbors_takes_the_exact_pass(engine, k):
+    """Beyond 60 neighbours there is no candidate kernel: every row goes through the exact pass over all keys."""
+    asm = synth.s1_families(400, seed=6)
+    res = _run(engine, asm, "5p6", k, "tc")
+    assert res["uncertified"] == asm.n
+    cols, prof = ko.profile_np(asm.as_dict(), "5p6")
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+
+
+def _exact_d2(counts, key_len, i, js):
+    from fractions import Fraction
+    ci, li = [int(v) for v in counts[i]], int(key_len[i])
+    out = []
+    for j in js:
+        cj, lj = [int(v) for v in counts[j]], int(key_len[j])
+        out.append(Fraction(sum((a * lj - b * li) ** 2 for a, b in zip(ci, cj)), (li * lj) ** 2))
+    return out
+
+
+def test_certificate_sends_mass_duplicates_to_the_exact_pass(engine):
+    """More exact duplicates than the candidate list is wide: the fp32 candidate ranking cannot tell which of
+    them it dropped, K5 must not certify those rows, and the exact pass returns the canonical answer
+    (self, then (distance, index))."""
+    rng = np.random.default_rng(23)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    dup = rnd(1800)
+    seqs = [rnd(int(x)) for x in rng.integers(300, 2500, 300)]
+    pos = sorted(rng.choice(300, 40, replace=False).tolist())
+    for p_ in pos:
+        seqs[p_] = dup
+    asm = _assembly_from(seqs)
+    asm.key_len[:] = 11                                    # equal header lengths: the duplicates' profile rows are identical
+    res = profile_and_knn(engine, asm.bases, asm.offsets, asm.key_len, "5p6", n_neighbors=3, impl=IMPLS["tc"])
+    assert res["uncertified"] >= 40
+    idx = res["knn_idx"]
+    for p_ in pos:
+        others = [q for q in pos if q != p_][:2]
+        assert idx[p_].tolist() == [p_] + others, (p_, idx[p_])
+        assert (res["knn_dist"][p_] == 0).all()
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, "5p6")
+    prof = counts / asm.key_len[:, None].astype(np.float64)
+    rep = knn_oracle.check_knn(idx, res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+
+
+def test_certificate_near_ties_of_long_contigs(engine):
+    """Adversarial case of the candidate width: 48 variants of one 15 kb contig, one substitution each.  Their
+    distances to each other differ in the 7th digit while the fp32 scores are of magnitude n/l, so the
+    candidate ranking is noise.  Whatever K5 certifies or hands to the exact pass, the k distances returned
+    must be EXACTLY the k smallest exact-rational distances."""
+    rng = np.random.default_rng(29)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    base = rnd(15000)
+    seqs = [rnd(int(x)) for x in rng.integers(300, 3000, 260)]
+    fam = []
+    for v in range(48):
+        p_ = int(rng.integers(10, 14990))
+        b = base[p_]
+        seqs.append(base[:p_] + "ACGT"[("ACGT".index(b) + 1 + v % 3) % 4] + base[p_ + 1:])
+        fam.append(len(seqs) - 1)
+    asm = _assembly_from(seqs)
+    k = 4
+    res = profile_and_knn(engine, asm.bases, asm.offsets, asm.key_len, "5p6", n_neighbors=k, impl=IMPLS["tc"])
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, "5p6")
+    for i in fam[::3]:
+        want_i, want_d = knn_oracle.knn_exact(counts, asm.key_len, k, rows=[i])
+        got = res["knn_idx"][i].tolist()
+        assert got[0] == i and len(set(got)) == k
+        got_d = sorted(float(x) for x in _exact_d2(counts, asm.key_len, i, got))
+        assert np.allclose(got_d, sorted(want_d[0].tolist()), rtol=1e-14, atol=0), (i, got, want_i)
+    prof = counts / asm.key_len[:, None].astype(np.float64)
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+
+
+def test_redundant_merge_200k_5120_k15(engine):
+    """BASELINE config 4's regime on one GPU: S2 (16-fold families, 10 % exact duplicates), 5120 dense columns,
+    n_neighbors = 15, 200 000 contigs.  1 024 sampled rows are checked against distances computed from the
+    integer counts (fp64 Gram of integers below 2^53: exact), every row structurally."""
+    n = 200000
+    asm = synth.s2_redundant(n, seed=11)
+    res = _run(engine, asm, "5+6", 15, "tc")
+    idx, dist = res["knn_idx"], res["knn_dist"]
+    assert idx.shape == (n, 15) and (idx[:, 0] == np.arange(n)).all() and (dist[:, 0] == 0).all()
+    assert (idx >= 0).all() and (idx < n).all() and (np.diff(dist[:, 1:], axis=1) >= 0).all()
+    rows = np.sort(np.random.default_rng(1).choice(n, 1024, replace=False))
+    prof = res["profile"]                                  # counts / len(key), bit-exact by the K1-K3 tests
+    l = asm.key_len.astype(np.float64)
+    c_rows = np.rint(prof[rows] * l[rows, None])
+    sq = np.empty(n)
+    gram = np.empty((len(rows), n))
+    for lo in range(0, n, 20000):
+        blk = np.rint(prof[lo:lo + 20000] * l[lo:lo + 20000, None])
+        sq[lo:lo + 20000] = np.einsum("ij,ij->i", blk, blk)
+        gram[:, lo:lo + 20000] = c_rows @ blk.T
+    num = sq[rows][:, None] * (l[None, :] ** 2) + sq[None, :] * (l[rows][:, None] ** 2) - 2.0 * gram * np.outer(l[rows], l)
+    truth = num / np.outer(l[rows], l) ** 2
+    rep = knn_oracle.check_knn(idx[rows], dist[rows], truth, rows=rows)
+    assert knn_oracle.parity_ok(rep), rep
