@@ -148,6 +148,8 @@ class Engine:
         self._up = None          # H2D stream of the chunked upload
         self._host = {}          # reusable pinned result buffers
         self._hold_stream = False
+        self.timing_enabled = False
+        self.last_uncertified = 0
         self._bind_stream()
 
     def close(self):
@@ -170,6 +172,7 @@ class Engine:
     # ---- timing / accounting -------------------------------------------------
     def enable_timing(self, on=True):
         check(self.lib.kb_enable_timing(self.ctx, 1 if on else 0))
+        self.timing_enabled = bool(on)
 
     def stage_ms(self, stage):
         """(mean ms, launches) of a stage since the last read; synchronises."""
@@ -697,3 +700,280 @@ def profile_and_knn(engine, bases, offsets, key_len, kmer_size="5p6", n_neighbor
         side.synchronize()
         out["profile"] = hold["profile"].numpy()
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# the pre-planned pass: static buffers, one enqueue, CUDA graph, peer-memory exchange
+# ---------------------------------------------------------------------------------------
+
+class _KnnXchg(ctypes.Structure):
+    """kb_knn_xchg of include/karma_b200.h"""
+    _fields_ = [("d_arrive", c_void_p), ("d_epoch", c_void_p), ("rows_per_src", c_int64), ("n_peers", ctypes.c_int32),
+                ("self_rank", ctypes.c_int32), ("d_peer_idx", c_void_p), ("d_peer_dist", c_void_p)]
+
+
+class _RawDevice:
+    """__cuda_array_interface__ view of raw device memory (the exchange arena is allocated by the library)."""
+
+    def __init__(self, addr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(addr), False), "version": 2}
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class PassPlan:
+    """The optimistic hot path (K1 -> K3 -> exchange -> K4 -> K5) of `_device_pass`, planned once for a shape and
+    then re-run with ONE enqueue: every buffer is static, nothing is allocated and nothing synchronises inside
+    a pass, so the pass can be (and by default is) captured in a CUDA graph.
+
+    Multi-GPU (one process per GPU): the exchange runs over peer memory (kb_xchg_*, NVLink): after K3 the operand
+    and row-record shards are pushed into every peer's arena on a side stream while K4 already sweeps the local
+    shard (its TMA producer waits for the arrival flag of a shard before its first key tile); K5 stores the
+    k-lists into every peer's gathered result arrays.  No NCCL call is on the path; `group` is used once, to
+    hand the IPC handles round.
+
+    A pass is validated afterwards from a few words per rank (flags OR, uncertified rows, presence summary):
+    `run()` enqueues pass i and returns a token; `check(token)` waits for that pass only -- call it after the
+    next `run()` to keep the GPU busy.  If the optimistic assumptions fail (non-ACGT bytes, a missing column, a
+    row beyond the exact range of the tensor path) `check` returns False and the caller redoes the input with
+    `device_pass(..., optimistic=False)`; rows K5 could not certify are redone in place (exact pass)."""
+
+    def __init__(self, engine, n, total_bases, kmer_size="5p6", n_neighbors=None, impl=_lib.KB_KNN_TC,
+                 want_profile=True, group=None, rank=0, world=1, n_total=None, graph=True):
+        self.engine = engine
+        self.lib = engine.lib
+        dev = engine.device
+        self.n, self.k, self.world, self.rank, self.group = int(n), n_neighbors, int(world), int(rank), group
+        self.multi = group is not None and world > 1
+        self.n_total = int(n_total) if self.multi else self.n
+        self.mode = mode_of(kmer_size)
+        self.kmer_size = kmer_size
+        self.faithful = self.mode == KB_MODE_5P6 or self.mode >= 16
+        self.cols = check(self.lib.kb_mode_columns(self.mode))
+        self.dp = _round_up(self.cols, 64)
+        self.per = shard_bounds(self.n_total, self.world, self.rank)[2] if self.multi else self.n
+        self.q_row0 = self.rank * self.per if self.multi else 0
+        self.nk = self.per * self.world if self.multi else self.n
+        self.impl = impl if impl != KB_KNN_AUTO else (_lib.KB_KNN_TC if self.nk >= 512 else _lib.KB_KNN_SIMT)
+        self.want_knn = n_neighbors is not None
+        k = self.k or 1
+        # inputs
+        cap = _round_up(int(total_bases), 16) + 32
+        self.d_bases = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        self.d_offsets = torch.zeros(self.n + 1, dtype=torch.int64, device=dev)
+        self.d_key_len = torch.ones(max(self.n, 1), dtype=torch.int32, device=dev)
+        # K1 / K3 products
+        self.counts = torch.empty((self.n, self.cols), dtype=torch.int32, device=dev)
+        self.exotic = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
+        self.presence = torch.zeros(self.cols + 1, dtype=torch.int32, device=dev)
+        self.profile = torch.empty((self.n, self.cols), dtype=torch.float64, device=dev) if want_profile else None
+        self.x = None
+        self.side = None
+        if self.multi and self.want_knn:
+            self._setup_exchange(k)
+        else:
+            self.operand_all = torch.empty((self.nk, self.dp), dtype=torch.float16, device=dev) if self.want_knn else None
+            self.rowmeta_all = torch.empty((self.nk, 8), dtype=torch.int32, device=dev)
+            self.all_idx = torch.empty((self.nk, k), dtype=torch.int32, device=dev) if self.want_knn else None
+            self.all_dist = torch.empty((self.nk, k), dtype=torch.float32, device=dev) if self.want_knn else None
+            self.rec_all = torch.zeros((1, 4), dtype=torch.int32, device=dev)
+        self.idx = self.all_idx[self.q_row0:self.q_row0 + self.n] if self.want_knn else None
+        self.dist = self.all_dist[self.q_row0:self.q_row0 + self.n] if self.want_knn else None
+        self.rec = self.rec_all[self.rank if self.x is not None else 0]      # [flags OR, uncertified rows, presence[D], 0]
+        self.ws = None
+        self._unc = None
+        if self.want_knn:
+            need = check(self.lib.kb_knn_workspace_bytes(engine.ctx, self.n, self.nk, self.q_row0, self.dp, self.k, self.impl, 0))
+            self.ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = c_void_p()
+            check(self.lib.kb_knn_uncertified_ptr(engine.ctx, self.n, self.nk, self.q_row0, self.dp, self.k, self.impl, 0,
+                                                  ptr(self.ws), byref(out)))
+            off = out.value - self.ws.data_ptr()
+            self._unc = self.ws[off:off + 4].view(torch.int32)
+        self.h_val = [torch.zeros((self.rec_all.shape[0], 4), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._step = 0
+        self.graph = None
+        self._want_graph = bool(graph)
+
+    # ---- exchange set-up (once) -----------------------------------------------------------
+    def _setup_exchange(self, k):
+        import torch.distributed as dist
+        dev = self.engine.device
+        W, per, dp = self.world, self.per, self.dp
+        off = 1024
+        lay = {}
+        for name, nbytes in (("operand", W * per * dp * 2), ("rowmeta", W * per * 32), ("idx", W * per * k * 4),
+                             ("dist", W * per * k * 4), ("rec", W * 16)):
+            lay[name] = off
+            off = _round_up(off + nbytes, 256)
+        self._lay, total = lay, off
+        x, local = c_void_p(), c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        rc = self.lib.kb_xchg_create(self.engine.ctx, W, self.rank, total, byref(x), byref(local), handle)
+        mine = bytes(handle) if rc == 0 else None
+        err = None if rc == 0 else self.lib.kb_last_error().decode("utf-8", "replace")
+        got = [None] * W
+        dist.all_gather_object(got, (mine, err), group=self.group)
+        if any(h is None for h, _ in got):
+            raise _lib.KarmaB200Error(-2, "peer-memory arena could not be created on every rank: %r" % ([e for _, e in got],))
+        rc = self.lib.kb_xchg_attach(x, b"".join(h for h, _ in got))
+        err = None if rc == 0 else self.lib.kb_last_error().decode("utf-8", "replace")
+        got = [None] * W
+        dist.all_gather_object(got, err, group=self.group)
+        if any(e is not None for e in got):
+            raise _lib.KarmaB200Error(-2, "peer-memory arenas could not be mapped on every rank: %r" % (got,))
+        self.x = x
+        base = local.value
+        arena = torch.as_tensor(_RawDevice(base, total), device=dev)
+        self._arena = arena
+
+        def view(name, nbytes, dtype, shape):
+            return arena[lay[name]:lay[name] + nbytes].view(dtype).view(shape)
+        self.operand_all = view("operand", W * per * dp * 2, torch.float16, (W * per, dp))
+        self.rowmeta_all = view("rowmeta", W * per * 32, torch.int32, (W * per, 8))
+        self.all_idx = view("idx", W * per * k * 4, torch.int32, (W * per, k))
+        self.all_dist = view("dist", W * per * k * 4, torch.float32, (W * per, k))
+        self.rec_all = view("rec", W * 16, torch.int32, (W, 4))
+        self.rec_all.zero_()
+        # peers' gathered result arrays as seen from here (K5 stores its rows there)
+        pi, pd = [], []
+        for p in range(W):
+            if p == self.rank:
+                continue
+            pp = c_void_p()
+            check(self.lib.kb_xchg_peer_ptr(x, p, byref(pp)))
+            pi.append(pp.value + lay["idx"])
+            pd.append(pp.value + lay["dist"])
+        self._peer_idx = torch.tensor(pi, dtype=torch.int64, device=dev)
+        self._peer_dist = torch.tensor(pd, dtype=torch.int64, device=dev)
+        arrive, epoch = c_void_p(), c_void_p()
+        check(self.lib.kb_xchg_flags(x, byref(arrive), byref(epoch)))
+        self._xchg = _KnnXchg(arrive.value, epoch.value, per, W - 1, self.rank, self._peer_idx.data_ptr(), self._peer_dist.data_ptr())
+        self._regions = ((ctypes.c_int64 * 2)(lay["operand"], lay["rowmeta"]), (ctypes.c_int64 * 2)(per * dp * 2, per * 32))
+        self.side = torch.cuda.Stream(dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.x is not None:
+            torch.cuda.synchronize(self.engine.device)
+            self.graph = None
+            self.lib.kb_xchg_destroy(self.x)
+            self.x = None
+
+    # ---- inputs ---------------------------------------------------------------------------
+    def load(self, bases, offsets, key_len):
+        """Copy this rank's contigs (host or device tensors / arrays) into the plan's input buffers."""
+        def t(a, dtype):
+            return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+        o = t(offsets, np.int64)
+        total = int(o[-1])
+        if o.numel() != self.n + 1 or _round_up(total, 16) + 32 > self.d_bases.numel():
+            raise ValueError("PassPlan was planned for %d contigs / %d bases" % (self.n, self.d_bases.numel() - 32))
+        self.d_bases[:total].copy_(t(bases, np.uint8)[:total], non_blocking=True)
+        self.d_offsets.copy_(o, non_blocking=True)
+        if self.n:
+            self.d_key_len.copy_(t(key_len, np.int32), non_blocking=True)
+
+    # ---- one pass ---------------------------------------------------------------------------
+    def enqueue(self):
+        """K1 -> K3 -> [push] -> K4 -> K5 -> [finish] on the current stream.  No allocation, no synchronisation."""
+        e, lib = self.engine, self.lib
+        e._bind_stream()
+        main = torch.cuda.current_stream(e.device)
+        if self.x is not None:
+            check(lib.kb_xchg_begin(self.x))
+        self.presence.zero_()
+        self.rec.zero_()
+        if self.n:
+            check(lib.kb_count(e.ctx, self.mode | KB_COUNT_NO_COLUMNS, ptr(self.d_bases), ptr(self.d_offsets), self.n,
+                               ptr(self.counts), self.counts.stride(0), ptr(self.exotic), ptr(self.presence)))
+        n_alloc = self.per if self.x is not None else self.n
+        lo = self.q_row0
+        check(lib.kb_normalise(e.ctx, ptr(self.counts) if self.n else None, self.counts.stride(0), self.cols,
+                               ptr(self.d_key_len) if self.n else None, self.n, n_alloc,
+                               ptr(self.profile) if self.profile is not None and self.n else None, self.cols,
+                               ptr(self.operand_all[lo:]) if self.want_knn else None, self.dp,
+                               ptr(self.rowmeta_all[lo:]), ptr(self.presence), ptr(self.rec)))
+        if self.x is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
+            check(lib.kb_xchg_push(self.x, c_void_p(self.side.cuda_stream), 2, self._regions[0], self._regions[1]))
+        if self.want_knn and self.n:
+            check(lib.kb_knn(e.ctx, self.impl, self.k, ptr(self.operand_all), self.dp, self.dp, ptr(self.rowmeta_all),
+                             self.nk, self.q_row0, self.n, None, None, 0, 0, 0, ptr(self.idx), ptr(self.dist), None,
+                             ptr(self.ws), self.ws.numel(), byref(self._xchg) if self.x is not None else None))
+            self.rec[1:2].copy_(self._unc, non_blocking=True)
+        self.rec[2:3].copy_(self.presence[self.cols:], non_blocking=True)
+        if self.x is not None:
+            check(lib.kb_xchg_finish(self.x, self._lay["rec"], 4))
+            main.wait_stream(self.side)
+
+    def capture(self, warmup=2):
+        """Warm up eagerly (uploads the K4 piece table, sizes scratch buffers), then capture the pass in a CUDA
+        graph.  Every rank must call this at the same point."""
+        e = self.engine
+        timing = e.timing_enabled
+        e.enable_timing(False)
+        for _ in range(warmup):
+            self.enqueue()
+        torch.cuda.synchronize(e.device)
+        if self._want_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue()
+            self.graph = g
+            e._bind_stream()
+        torch.cuda.synchronize(e.device)
+        e.enable_timing(timing)
+
+    def run(self):
+        """Enqueue one pass (graph replay when captured) plus the copy of the validation words; returns a token."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.enqueue()
+        slot = self._step & 1
+        self.h_val[slot].copy_(self.rec_all, non_blocking=True)
+        self._events[slot].record(torch.cuda.current_stream(self.engine.device))
+        self._step += 1
+        return self._step - 1
+
+    def check(self, token):
+        """Wait for pass `token` (the latest or the one before) and read its validation words.
+        Returns dict(ok, flags_or, uncertified, exotic, complete)."""
+        if token < self._step - 2:
+            raise ValueError("the validation words of that pass have been overwritten")
+        slot = token & 1
+        self._events[slot].synchronize()
+        v = self.h_val[slot].numpy()
+        flags_or = int(np.bitwise_or.reduce(v[:, 0]))
+        unc = int(v[:, 1].sum())
+        last = int(np.bitwise_or.reduce(v[:, 2] & 1)) | (2 if (v[:, 2] & 2).any() else 0)
+        exo, complete = bool(last & 1), bool(last & 2)
+        if not complete and not self.multi:
+            complete = bool(self.presence[:-1].cpu().numpy().all())
+        ok = not exo and (complete or not self.faithful) and not (self.want_knn and (flags_or & 3)) and not (flags_or & 4)
+        return {"ok": ok, "flags_or": flags_or, "uncertified": unc, "exotic": exo, "complete": complete}
+
+    def fixup(self):
+        """Exact pass over the rows K5 could not certify (all ranks call it when any rank has such rows);
+        the patched rows are shared again.  Synchronises."""
+        e = self.engine
+        e._bind_stream()
+        n = check(self.lib.kb_knn_fixup(e.ctx, self.impl, self.k, ptr(self.operand_all), self.dp, self.dp, ptr(self.rowmeta_all),
+                                        self.nk, self.q_row0, self.n, None, None, 0, 0, 0, ptr(self.idx), ptr(self.dist), None,
+                                        ptr(self.ws), self.ws.numel()))
+        if self.multi:
+            import torch.distributed as dist
+            for t in (self.all_idx, self.all_dist):
+                shard = t[self.q_row0:self.q_row0 + self.per].clone()
+                dist.all_gather_into_tensor(t, shard, group=self.group)
+        return int(n)
+
+    def columns(self):
+        return mode_column_names(self.mode)

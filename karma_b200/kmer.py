@@ -32,7 +32,86 @@ except Exception:                       # stand-alone: same format as karma/logs
     logger.setLevel(logging.INFO)
 
 
+def _accepts(fn, *names):
+    import inspect
+    try:
+        params = inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
+    if any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values()):
+        return True
+    return all(n in params for n in names)
+
+
+def umap_embedding(profile, knn_indices, knn_dists, umap_args, umap_module=None):
+    """The call of kmer.py:285-290, ``umap.UMAP(**umap_args).fit_transform(profile)``, fed with the exact
+    kNN graph from the GPU so that UMAP does not search for neighbours again.  Three hand-off routes, chosen
+    by FEATURE (signatures), never by catching errors out of ``fit_transform``:
+
+    1. umap-learn >= 0.5: ``UMAP(precomputed_knn=(idx, dist[, None]))``.  0.5.0-0.5.3 insist on an NNDescent
+       object as third element; the parameters are validated up front (``_validate_parameters``) and a
+       rejection falls through to the next route.
+    2. umap-learn 0.3.x / 0.4.x -- the reference pins 0.3.9 (conda/meta.yaml:15): the stages ``UMAP.fit``
+       itself runs, ``umap.umap_.fuzzy_simplicial_set(..., knn_indices=, knn_dists=)`` followed by
+       ``simplicial_set_embedding`` with UMAP's defaults (spread 1, learning rate 1, repulsion 1, 5 negative
+       samples, spectral init, default epochs), on the float32 copy of the profile as ``fit`` makes it.
+    3. neither available (or no graph: fewer contigs than neighbours): the stock call.
+
+    Returns (embedding, route) with route in {"precomputed_knn", "fuzzy_simplicial_set", "stock"}."""
+    if umap_module is None:
+        import umap as umap_module
+    n = profile.shape[0]
+    k = umap_args["n_neighbors"]
+    have_graph = knn_indices is not None and knn_dists is not None and knn_indices.shape == (n, k) and k < n
+    if have_graph and _accepts(umap_module.UMAP.__init__, "precomputed_knn"):
+        idx = np.ascontiguousarray(knn_indices, dtype=np.int64)
+        dst = np.ascontiguousarray(knn_dists, dtype=np.float32)
+        for graph in ((idx, dst), (idx, dst, None)):
+            try:
+                reducer = umap_module.UMAP(precomputed_knn=graph, **umap_args)
+                if hasattr(reducer, "_validate_parameters"):
+                    reducer._validate_parameters()
+            except (TypeError, ValueError):
+                continue
+            return reducer.fit_transform(profile), "precomputed_knn"
+    um = getattr(umap_module, "umap_", None)
+    fss = getattr(um, "fuzzy_simplicial_set", None)
+    sse = getattr(um, "simplicial_set_embedding", None)
+    fab = getattr(um, "find_ab_params", None)
+    if (have_graph and fss is not None and sse is not None and fab is not None and
+            _accepts(fss, "X", "n_neighbors", "random_state", "metric", "knn_indices", "knn_dists") and
+            _accepts(sse, "data", "graph", "n_components", "initial_alpha", "a", "b", "gamma", "negative_sample_rate",
+                     "n_epochs", "init", "random_state", "metric", "metric_kwds") and
+            not _accepts(sse, "densmap")):
+        from sklearn.utils import check_array, check_random_state
+        x = check_array(profile, dtype=np.float32, accept_sparse="csr")          # UMAP.fit's own cast
+        rs = check_random_state(umap_args.get("random_state"))
+        a, b = fab(1.0, umap_args["min_dist"])
+        fss_kw = dict(X=x, n_neighbors=k, random_state=rs, metric="euclidean", metric_kwds={},
+                      knn_indices=np.ascontiguousarray(knn_indices, dtype=np.int64),
+                      knn_dists=np.ascontiguousarray(knn_dists, dtype=np.float32),
+                      angular=False, set_op_mix_ratio=1.0, local_connectivity=1.0, verbose=False)
+        import inspect
+        fss_kw = {kk: v for kk, v in fss_kw.items() if kk in inspect.signature(fss).parameters}
+        graph = fss(**fss_kw)
+        if isinstance(graph, tuple):                                              # 0.4.x returns (graph, sigmas, rhos)
+            graph = graph[0]
+        sse_kw = dict(data=x, graph=graph, n_components=umap_args["n_components"], initial_alpha=1.0, a=a, b=b, gamma=1.0,
+                      negative_sample_rate=5, n_epochs=0, init="spectral", random_state=rs, metric="euclidean",
+                      metric_kwds={}, verbose=False)
+        sse_kw = {kk: v for kk, v in sse_kw.items() if kk in inspect.signature(sse).parameters}
+        emb = sse(**sse_kw)
+        if isinstance(emb, tuple):
+            emb = emb[0]
+        return emb, "fuzzy_simplicial_set"
+    return umap_module.UMAP(**umap_args).fit_transform(profile), "stock"
+
+
 class KmerClustering:
+    """Mirror of kmer.py's class.  ``kmer_size``: "5p6" (kmer.py's default), any integer k >= 1 (kmer.py:83-85;
+    k <= 7 count into dense shared-memory histograms, larger k through sorted k-mer codes), or the fixed-column
+    throughput shapes "5+6" / "4+5" of this library (A/C/G/T only: other bytes are rejected there)."""
+
     def __init__(self, sequences, output_dir, kmer_size, threads):
         # kmer.py:15-27
         self.sequences = sequences
@@ -175,18 +254,17 @@ class KmerClustering:
             return
 
         logger.info("Calculate kmer profiles.")
-        profile = self.__calc_kmer_profile(n_neighbors=neighbors)
+        # the exact kNN graph comes out of the same GPU pass when it can replace UMAP's own neighbour search:
+        # an integer n_neighbors below the number of contigs (UMAP truncates it itself otherwise)
+        want_graph = isinstance(neighbors, (int, np.integer)) and not isinstance(neighbors, bool) and \
+            1 <= neighbors < len(self.sequences)
+        profile = self.__calc_kmer_profile(n_neighbors=int(neighbors) if want_graph else None)
 
         logger.info("Dimension reduction with UMAP.")
-        import umap
         umap_args = {"n_neighbors": neighbors, "n_components": components, "min_dist": dist, "random_state": r_state}
-        try:
-            # umap-learn >= 0.5 accepts the exact graph (self in column 0, euclidean distances)
-            graph = (self.knn_indices.astype(np.int64), self.knn_dists, None)
-            embedding = umap.UMAP(precomputed_knn=graph, **umap_args).fit_transform(profile)
-        except TypeError:
-            # umap-learn 0.3.9 (conda/meta.yaml:15) has no such argument: the call of kmer.py:285-290
-            embedding = umap.UMAP(**umap_args).fit_transform(profile)
+        embedding, self.umap_route = umap_embedding(profile, self.knn_indices, self.knn_dists, umap_args)
+        if self.umap_route == "stock":
+            logger.debug("UMAP computed its own neighbour graph (no hand-off route in this umap-learn).")
 
         logger.info(f"Perform clustering with HDBSCAN. (min_cluster_size: {min_cluster_size})")
         import hdbscan

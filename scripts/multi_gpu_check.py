@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from karma_b200 import _lib, synth  # noqa: E402
-from karma_b200.engine import Engine, profile_and_knn, shard_bounds  # noqa: E402
+from karma_b200.engine import Engine, PassPlan, profile_and_knn, shard_bounds  # noqa: E402
 
 
 def main():
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--synth", default="S1")
     ap.add_argument("--kmer", default="5p6")
     ap.add_argument("--exotic", action="store_true", help="inject N / lowercase bases into contigs of different ranks")
+    ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -47,13 +48,42 @@ def main():
     shard = asm.slice(lo, hi)
     res = profile_and_knn(eng, shard.bases, shard.offsets, shard.key_len, kmer, n_neighbors=a.neighbors,
                           impl=_lib.KB_KNN_TC, group=dist.group.WORLD, rank=rank, world=world, row0=lo, n_total=asm.n)
+    # the pre-planned pass: peer-memory exchange, three passes back to back (eager, eager, CUDA graph replay);
+    # every rank must end up with ALL k-lists, and its own rows must equal the eager / NCCL path bit for bit
+    plan_ok = True
+    if not a.exotic and shard.n > 0:
+        plan = PassPlan(eng, shard.n, int(shard.offsets[-1]), kmer, n_neighbors=a.neighbors, impl=_lib.KB_KNN_TC,
+                        group=dist.group.WORLD, rank=rank, world=world, n_total=asm.n, graph=not a.no_graph)
+        plan.load(shard.bases, shard.offsets, shard.key_len)
+        plan.capture(warmup=2)
+        for it in range(3):
+            tok = plan.run()
+            chk = plan.check(tok)
+            if chk["uncertified"]:
+                plan.fixup()
+            torch.cuda.synchronize()
+            mine_i = plan.idx.cpu().numpy(); mine_d = plan.dist.cpu().numpy()
+            same = np.array_equal(mine_i, res["knn_idx"]) and np.array_equal(mine_d, res["knn_dist"]) and chk["ok"]
+            prof_same = plan.profile.cpu().numpy().tobytes() == res["profile"].tobytes()
+            plan_ok &= same and prof_same
+            print("rank %d plan pass %d: own rows == eager path %s, profile %s, check %r" % (rank, it, same, prof_same, chk))
+        plan_all_idx = plan.all_idx.cpu().numpy()[:asm.n]
+        plan_all_dist = plan.all_dist.cpu().numpy()[:asm.n]
+        plan.close()
+    else:
+        plan_all_idx = plan_all_dist = None
     # gather the shards' results on rank 0 (object gather: this is a test, not the data path)
     gathered = [None] * world
-    dist.gather_object((lo, hi, res["columns"], res["profile"], res["knn_idx"], res["knn_dist"]), gathered if rank == 0 else None, dst=0)
+    dist.gather_object((lo, hi, res["columns"], res["profile"], res["knn_idx"], res["knn_dist"], plan_ok, plan_all_idx, plan_all_dist),
+                       gathered if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
         full = profile_and_knn(eng, asm.bases, asm.offsets, asm.key_len, kmer, n_neighbors=a.neighbors, impl=_lib.KB_KNN_TC)
-        for (glo, ghi, cols, prof, idx, dst) in gathered:
+        for gr, (glo, ghi, cols, prof, idx, dst, p_ok, p_idx, p_dst) in enumerate(gathered):
+            if p_idx is not None:
+                all_same = np.array_equal(p_idx, full["knn_idx"]) and np.array_equal(p_dst, full["knn_dist"])
+                print("rank %d: planned passes ok %s, gathered lists of ALL rows == single GPU %s" % (gr, p_ok, all_same))
+                ok &= bool(p_ok) and all_same
             same_cols = cols == full["columns"]
             same_prof = prof.tobytes() == full["profile"][glo:ghi].tobytes()
             same_idx = np.array_equal(idx, full["knn_idx"][glo:ghi])

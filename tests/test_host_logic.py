@@ -126,8 +126,8 @@ def test_run_flow_with_stubbed_umap_hdbscan(tmp_path, monkeypatch):
     monkeypatch.setattr(k, "_KmerClustering__calc_kmer_profile", fake_profile)
     k.run(neighbors=2, components=10, dist=0, r_state=42, min_cluster_size=2)
     assert seen["umap"]["n_neighbors"] == 2 and seen["umap"]["random_state"] == 42
-    idx, dst, _ = seen["umap"]["precomputed_knn"]
-    assert idx.shape == (4, 2) and dst.dtype == np.float32
+    idx, dst = seen["umap"]["precomputed_knn"][:2]
+    assert idx.shape == (4, 2) and dst.dtype == np.float32 and k.umap_route == "precomputed_knn"
     assert seen["hdb"] == {"min_cluster_size": 2}
     assert k.unlabeled_cluster == [["c2"]] and sorted(k.clusters) == [["c0", "c1"], ["c3"]]
     lines = open(k.output_file).read().split("\n")
@@ -136,6 +136,132 @@ def test_run_flow_with_stubbed_umap_hdbscan(tmp_path, monkeypatch):
     assert ev[0].split("\t") == ["kmer_size", "n_neighbors", "n_components", "min_dist", "random_state",
                                  "min_cluster_size", "unlabeled", "no_groups", "mean_probability"]
     assert ev[1].split("\t")[:7] == ["5p6", "2", "10", "0", "42", "2", "1"]
+
+
+def _fake_umap_039(seen):
+    """A module with the signatures of umap-learn 0.3.9 (the version conda/meta.yaml:15 pins): UMAP has no
+    precomputed_knn; umap.umap_ offers the stages UMAP.fit runs."""
+    class UMAP:
+        def __init__(self, n_neighbors=15, n_components=2, metric="euclidean", n_epochs=None, learning_rate=1.0,
+                     init="spectral", min_dist=0.1, spread=1.0, set_op_mix_ratio=1.0, local_connectivity=1.0,
+                     repulsion_strength=1.0, negative_sample_rate=5, transform_queue_size=4.0, a=None, b=None,
+                     random_state=None, metric_kwds=None, angular_rp_forest=False, target_n_neighbors=-1,
+                     target_metric="categorical", target_metric_kwds=None, target_weight=0.5, transform_seed=42,
+                     verbose=False):
+            seen["stock_ctor"] = dict(n_neighbors=n_neighbors, n_components=n_components, min_dist=min_dist, random_state=random_state)
+
+        def fit_transform(self, x):
+            seen["stock_fit"] = x
+            return np.zeros((x.shape[0], 2))
+
+    def fuzzy_simplicial_set(X, n_neighbors, random_state, metric, metric_kwds={}, knn_indices=None, knn_dists=None,
+                             angular=False, set_op_mix_ratio=1.0, local_connectivity=1.0, verbose=False):
+        seen["fss"] = dict(X=X, n_neighbors=n_neighbors, metric=metric, knn_indices=knn_indices, knn_dists=knn_dists,
+                           random_state=random_state)
+        return "GRAPH"
+
+    def simplicial_set_embedding(data, graph, n_components, initial_alpha, a, b, gamma, negative_sample_rate, n_epochs,
+                                 init, random_state, metric, metric_kwds, verbose):
+        seen["sse"] = dict(data=data, graph=graph, n_components=n_components, initial_alpha=initial_alpha, a=a, b=b, gamma=gamma,
+                           negative_sample_rate=negative_sample_rate, n_epochs=n_epochs, init=init, metric=metric)
+        return np.full((data.shape[0], n_components), 7.0)
+
+    def find_ab_params(spread, min_dist):
+        seen["ab"] = (spread, min_dist)
+        return 1.5, 0.9
+
+    return types.SimpleNamespace(UMAP=UMAP, umap_=types.SimpleNamespace(
+        fuzzy_simplicial_set=fuzzy_simplicial_set, simplicial_set_embedding=simplicial_set_embedding, find_ab_params=find_ab_params))
+
+
+def test_umap_039_handoff_through_fuzzy_simplicial_set():
+    """umap-learn 0.3.9 has no precomputed_knn argument: the GPU graph goes into fuzzy_simplicial_set and the
+    embedding stage is run as UMAP.fit runs it -- the stock neighbour search is never invoked."""
+    from karma_b200.kmer import umap_embedding
+    seen = {}
+    fake = _fake_umap_039(seen)
+    rng = np.random.default_rng(3)
+    prof = rng.random((30, 12))
+    idx = np.argsort(rng.random((30, 30)), axis=1)[:, :5].astype(np.int32)
+    dst = np.sort(rng.random((30, 5)).astype(np.float32), axis=1)
+    args = {"n_neighbors": 5, "n_components": 3, "min_dist": 0.0, "random_state": 42}
+    emb, route = umap_embedding(prof, idx, dst, args, umap_module=fake)
+    assert route == "fuzzy_simplicial_set" and "stock_fit" not in seen and "stock_ctor" not in seen
+    assert np.array_equal(seen["fss"]["knn_indices"], idx) and seen["fss"]["knn_indices"].dtype == np.int64
+    assert np.array_equal(seen["fss"]["knn_dists"], dst) and seen["fss"]["n_neighbors"] == 5 and seen["fss"]["metric"] == "euclidean"
+    assert seen["fss"]["X"].dtype == np.float32 and seen["fss"]["X"].shape == (30, 12)            # UMAP.fit's float32 cast
+    assert seen["ab"] == (1.0, 0.0)
+    assert seen["sse"]["graph"] == "GRAPH" and seen["sse"]["n_components"] == 3 and (seen["sse"]["a"], seen["sse"]["b"]) == (1.5, 0.9)
+    assert seen["sse"]["initial_alpha"] == 1.0 and seen["sse"]["gamma"] == 1.0 and seen["sse"]["negative_sample_rate"] == 5
+    assert seen["sse"]["n_epochs"] == 0 and seen["sse"]["init"] == "spectral"
+    assert emb.shape == (30, 3) and (emb == 7.0).all()
+    # the same draws from the seed as UMAP.fit: one RandomState shared by both stages
+    assert seen["fss"]["random_state"] is not None
+    # no usable graph (n_neighbors >= number of contigs): the stock call of kmer.py:285-290
+    seen.clear()
+    emb, route = umap_embedding(prof[:4], None, None, {"n_neighbors": 5, "n_components": 2, "min_dist": 0.0, "random_state": 1},
+                                umap_module=fake)
+    assert route == "stock" and seen["stock_ctor"]["n_neighbors"] == 5 and seen["stock_fit"].shape == (4, 12)
+
+
+def test_umap_05_rejecting_precomputed_knn_falls_to_the_next_route():
+    """umap-learn 0.5.0-0.5.3 reject a graph without an NNDescent index when the parameters are validated:
+    that is caught at validation, never out of fit_transform, and the stock call follows (0.5's staged functions
+    have a different signature)."""
+    from karma_b200.kmer import umap_embedding
+    calls = []
+
+    class UMAP:
+        def __init__(self, n_neighbors=15, n_components=2, min_dist=0.1, random_state=None, precomputed_knn=(None, None, None)):
+            self.precomputed_knn = precomputed_knn
+            calls.append(("ctor", precomputed_knn[0] is not None))
+
+        def _validate_parameters(self):
+            if self.precomputed_knn[0] is not None:
+                raise ValueError("precomputed_knn[2] (knn_search_index) must be an NNDescent object.")
+
+        def fit_transform(self, x):
+            calls.append(("fit", self.precomputed_knn[0] is not None))
+            if self.precomputed_knn[0] is not None:
+                raise TypeError("must not be reached with a rejected graph")
+            return np.zeros((x.shape[0], 2))
+
+    fake = types.SimpleNamespace(UMAP=UMAP)
+    prof = np.random.default_rng(0).random((10, 4))
+    idx = np.zeros((10, 3), dtype=np.int32); dst = np.zeros((10, 3), dtype=np.float32)
+    emb, route = umap_embedding(prof, idx, dst, {"n_neighbors": 3, "n_components": 2, "min_dist": 0.0, "random_state": 1}, umap_module=fake)
+    assert route == "stock" and calls[-1] == ("fit", False) and ("fit", True) not in calls
+
+
+def test_run_skips_the_gpu_graph_when_umap_would_truncate_n_neighbors(tmp_path, monkeypatch):
+    """n_neighbors >= number of contigs (UMAP truncates it itself) or a non-integer value: profile only, stock call."""
+    seen = {}
+
+    class UMAP:
+        def __init__(self, **kw):
+            seen["umap"] = kw
+
+        def fit_transform(self, x):
+            return x[:, :2]
+
+    class HDBSCAN:
+        def __init__(self, **kw):
+            pass
+
+        def fit(self, emb):
+            self.labels_ = np.array([0, 0, -1])
+            self.probabilities_ = np.ones(3)
+            return self
+    monkeypatch.setitem(sys.modules, "umap", types.SimpleNamespace(UMAP=UMAP))
+    monkeypatch.setitem(sys.modules, "hdbscan", types.SimpleNamespace(HDBSCAN=HDBSCAN))
+    k = KmerClustering({">a": "ACGTA", ">b": "ACGTT", ">c": "GGGGG"}, str(tmp_path), "5p6", 1)
+
+    def fake_profile(n_neighbors=None):
+        seen["n_neighbors"] = n_neighbors
+        return np.eye(3)
+    monkeypatch.setattr(k, "_KmerClustering__calc_kmer_profile", fake_profile)
+    k.run(neighbors=30, components=2, dist=0, r_state=1, min_cluster_size=2)
+    assert seen["n_neighbors"] is None and "precomputed_knn" not in seen["umap"] and k.umap_route == "stock"
 
 
 def test_knn_oracle_exact_vs_fp64():
