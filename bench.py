@@ -598,7 +598,9 @@ def run_ours(a):
 
     flops = 2.0 * n * n_total * d_cols                     # this rank's query rows x all keys
     ach_tf = flops / (gemm_ms / 1e3) / 1e12
-    count_bytes = float(shard.offsets[-1]) + 4.0 * n * cols_full
+    # the fused counting kernel (K1+K3, kb_count_profile): bases read once; profile row (f64), operand row (f16) and the
+    # 32-byte row record written once; the u32 count rows never reach HBM
+    count_bytes = float(shard.offsets[-1]) + n * (8.0 * cols_full + 2.0 * plan.dp + 32.0)
     ach_gbs = count_bytes / (count_ms / 1e3) / 1e9
     traffic = ncu_traffic("k4_tc") if world == 1 else None
     line = {
@@ -621,7 +623,7 @@ def run_ours(a):
                      "traffic": (traffic or {}).get("bytes"), "traffic_source": (traffic or {}).get("source"),
                      "peak_source": pk["source"] + ", bf16 burst; sustained %s" % pk["tflops_sustained"],
                      "flops_per_launch": flops, "launches_timed": gemm_n},
-        "roofline_count": {"bound": "hbm", "kernel": "k1_count", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        "roofline_count": {"bound": "hbm", "kernel": "k1_count_warp<fused> (K1+K3 in one kernel: bases -> f64 profile + f16 operand + row records)", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                            "frac": ach_gbs / pk["hbm_gbs"], "bytes_per_launch": count_bytes},
     }
     line.update(extras)

@@ -177,6 +177,18 @@ KB_API int kb_normalise(kb_ctx* ctx, const uint32_t* d_counts, int64_t ld, int32
                  void* d_operand, int64_t ld_operand,
                  kb_rowmeta* d_rowmeta, uint32_t* d_presence, uint32_t* d_flags_or);
 
+/* ---- K1+K3 fused ------------------------------------------------------------
+ * kb_count followed by kb_normalise in ONE kernel, for inputs whose column dictionary is the full ACGT set of
+ * the mode (what a real assembly gives: validate with d_presence / d_exotic afterwards, and fall back to
+ * kb_count + kb_exotic_* + kb_compact + kb_normalise when a column is missing or a non-ACGT byte was seen).
+ * The u32 count rows never go to HBM: every contig's shared-memory histogram is turned straight into its
+ * fp64 profile row (count / key_len, bit-identical to kb_normalise), its fp16 operand row and its row record.
+ * Arguments as in kb_count / kb_normalise; ld_profile / ld_operand >= the mode's column count; contigs of any
+ * length (no split path: the longer ones are binned by whole CTAs).  n == 0 with n_alloc > 0 writes padding only. */
+KB_API int kb_count_profile(kb_ctx* ctx, int mode, const uint8_t* d_bases, const int64_t* d_offsets, const int32_t* d_key_len,
+                     int64_t n, int64_t n_alloc, double* d_profile, int64_t ld_profile, void* d_operand, int64_t ld_operand,
+                     kb_rowmeta* d_rowmeta, uint32_t* d_exotic, uint32_t* d_presence, uint32_t* d_flags_or);
+
 /* OR of kb_rowmeta.flags over rows [0,n) (padding rows, bit3, excluded) into *d_out:
  * lets the host validate a whole pass by reading one word. */
 KB_API int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t n, uint32_t* d_out);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "kb_exotic_scatter": (c_int, [_P, _P, _P, c_int64]),
     "kb_compact": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32]),
     "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P]),
+    "kb_count_profile": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P]),
     "kb_rowmeta_flags_or": (c_int, [_P, _P, c_int64, _P]),
     "kb_knn_workspace_bytes": (c_int64, [_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int, c_int64]),
     "kb_knn": (c_int, [_P, c_int, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int64, c_int64,

@@ -29,6 +29,9 @@
 // Roofline: HBM.  Algorithmic bytes per contig = L (bases) + 4*cols (row).
 #include "kb_common.cuh"
 #include <cstdlib>
+#include <cstring>
+#include <climits>
+#include <type_traits>
 
 // Scheduling of the dynamic queue (warp-per-contig kernel):
 //   contigs longer than `threshold` bases take the split path, `chunk` window starts per work item;
@@ -297,6 +300,129 @@ __device__ __forceinline__ void publish_presence(uint32_t* __restrict__ presence
     }
 }
 
+// ---- fused K1+K3 (kb_count_profile): when the column dictionary is the full ACGT set (the optimistic pass), the
+// row never goes to HBM as u32 counts: the flush turns the shared-memory histogram straight into the fp64 profile
+// row (count / len(key), kmer.py:120,:213), the fp16 kNN operand row and the 32-byte row record.
+struct FuseOut {
+    const int32_t* key_len;
+    double* profile; int64_t ld_profile;       // nullable
+    __half* operand; int64_t ld_operand;       // nullable
+    kb_rowmeta* rowmeta;                       // nullable
+    uint32_t* flags_or;                        // nullable
+    int64_t n_alloc;                           // rows [n, n_alloc) of operand / rowmeta are written as gather padding
+};
+
+// count / len in IEEE fp64, correctly rounded, without a division per element: q = x*rcp, one residual correction
+// (Markstein): exact for every (count, len) pair this path can see (checked exhaustively for count <= 300000,
+// len <= 3000 and on 4e8 random pairs up to 2^31 / 2^20 against the true quotient).
+__device__ __forceinline__ double quot(uint32_t x, double len, double rcp) {
+    const double a = __uint2double_rn(x);
+    const double q = a * rcp;
+    const double r = fma(-len, q, a);
+    return fma(r, rcp, q);
+}
+
+template <int COLS, int NT>
+__device__ __forceinline__ void flush_fused(uint32_t* hist, int tid, int64_t row, const FuseOut& f, double len, double rcp,
+                                            unsigned long long& sq, uint32_t& mx, uint64_t& pres) {
+    constexpr int VEC = COLS / 4;
+    constexpr int ITERS = (VEC + NT - 1) / NT;
+    static_assert(COLS % 4 == 0 && ITERS * 4 <= 64, "row flush is 128-bit; presence bits live in one 64-bit register");
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * NT;
+        if (i < VEC) {
+            const uint4 r = *reinterpret_cast<uint4*>(hist + 4 * i);
+            *reinterpret_cast<uint4*>(hist + 4 * i) = make_uint4(0, 0, 0, 0);
+            sq += (unsigned long long)r.x * r.x + (unsigned long long)r.y * r.y + (unsigned long long)r.z * r.z +
+                  (unsigned long long)r.w * r.w;
+            mx = max(max(mx, r.x), max(r.y, max(r.z, r.w)));
+            pres |= (uint64_t)((r.x != 0) | ((r.y != 0) << 1) | ((r.z != 0) << 2) | ((r.w != 0) << 3)) << (4 * it);
+            if (f.profile) {
+                double2 a, b;
+                a.x = quot(r.x, len, rcp); a.y = quot(r.y, len, rcp);
+                b.x = quot(r.z, len, rcp); b.y = quot(r.w, len, rcp);
+                double* q = f.profile + row * f.ld_profile + 4 * i;
+                if ((f.ld_profile & 1) == 0) {
+                    __stcs(reinterpret_cast<double2*>(q), a); __stcs(reinterpret_cast<double2*>(q) + 1, b);
+                } else {
+                    q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+                }
+            }
+            if (f.operand) {
+                const __half2 h0 = __floats2half2_rn((float)min(r.x, 2048u), (float)min(r.y, 2048u));
+                const __half2 h1 = __floats2half2_rn((float)min(r.z, 2048u), (float)min(r.w, 2048u));
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(f.operand + row * f.ld_operand + 4 * i) = pk;
+            }
+        }
+    }
+    if (f.operand)                                                       // zero padding of the operand row
+        for (int64_t c = COLS + tid; c < f.ld_operand; c += NT) f.operand[row * f.ld_operand + c] = __float2half_rn(0.f);
+}
+
+__device__ __forceinline__ void write_rowmeta(const FuseOut& f, int64_t row, unsigned long long sq, uint32_t mx, int32_t klen) {
+    const int flags = (mx > 2048u ? 1 : 0) | (sq >= (1ull << 24) ? 2 : 0) | (mx == 0 ? 4 : 0);
+    if (f.rowmeta) {
+        const double len = (double)klen;
+        kb_rowmeta m;
+        m.sqnorm = (double)sq; m.key_len = klen; m.flags = flags;
+        if (flags & 3) { m.cm_x = 0.f; m.cm_y = __int_as_float(0x7f800000); }          // K4 never proposes the row
+        else { m.cm_x = (float)(-2.0 / len); m.cm_y = (float)((double)sq / (len * len)); }
+        m.reserved[0] = m.reserved[1] = 0;
+        f.rowmeta[row] = m;
+    }
+    if (f.flags_or && flags) atomicOr(f.flags_or, (uint32_t)flags);
+}
+
+__device__ __forceinline__ void write_padding_rows(const FuseOut& f, int64_t n, int tid, int nthreads) {
+    for (int64_t row = n; row < f.n_alloc; ++row) {
+        if (f.operand)
+            for (int64_t c = tid; c < f.ld_operand; c += nthreads) f.operand[row * f.ld_operand + c] = __float2half_rn(0.f);
+        if (tid == 0 && f.rowmeta) {
+            kb_rowmeta m;
+            m.sqnorm = 0.0; m.key_len = 1; m.flags = 11;
+            m.cm_x = 0.f; m.cm_y = __int_as_float(0x7f800000);
+            m.reserved[0] = m.reserved[1] = 0;
+            f.rowmeta[row] = m;
+        }
+    }
+}
+
+// presence bits of one flush layout (NT threads) -> per-column bytes
+template <int COLS, int NT>
+__device__ __forceinline__ void presence_to_bytes(uint8_t* col, int tid, uint64_t pres) {
+    constexpr int VEC = COLS / 4;
+    constexpr int ITERS = (VEC + NT - 1) / NT;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * NT;
+        if (i < VEC) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((pres >> (4 * it + j)) & 1) col[4 * i + j] = 1;
+        }
+    }
+}
+// per-CTA column bytes -> presence vector: a CTA that saw every column proves the dictionary complete with one
+// store (bit 1 of presence[COLS]); otherwise per-column stores, checked before writing
+template <int COLS>
+__device__ __forceinline__ void publish_bytes(const uint8_t* col, uint32_t* __restrict__ presence, int* s_cnt, int tid, int nthreads) {
+    int mine = 0;
+    for (int c = tid; c < COLS; c += nthreads) mine += col[c];
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL, mine, o);
+    if ((tid & 31) == 0 && mine) atomicAdd(s_cnt, mine);
+    __syncthreads();
+    if (*s_cnt == COLS) {
+        if (tid == 0 && !(__ldcg(presence + COLS) & 2u)) atomicOr(presence + COLS, 2u);
+    } else {
+        for (int c = tid; c < COLS; c += nthreads)
+            if (col[c] && __ldcg(presence + c) == 0u) presence[c] = 1u;
+    }
+}
+
 // scratch (int32 words): [0] next row, [1] unused, [2..3] exotic total (u64),
 //   [4..5] u64: (number of long contigs << 32) | total number of chunks,
 //   [6 + 2i], [7 + 2i]: row and first chunk number of the i-th long contig (ascending in both)
@@ -315,11 +441,11 @@ __device__ __forceinline__ void queue_long(int32_t* scratch, int64_t row, int64_
 // into one histogram (a single warp needs 2-3 us per span with its scheduler shared: a 15 kb contig
 // would take 60-90 us alone).  The tickets after that are per warp: the remaining contigs, lp.batch
 // consecutive rows at a time, no block barriers.
-template <int KA, int KB, bool PALB, bool SORTED, int WARPS, bool TRACK, int MINB>
+template <int KA, int KB, bool PALB, bool SORTED, int WARPS, bool TRACK, int MINB, bool FUSE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
               uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-              uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp) {
+              uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp, FuseOut fuse) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     constexpr int THREADS = WARPS * 32;
     extern __shared__ __align__(16) uint32_t smem_hist[];
@@ -328,6 +454,9 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
     __shared__ int32_t s_row[32];
     __shared__ int s_n;
     __shared__ uint32_t s_red[WARPS];
+    __shared__ unsigned long long s_sq[WARPS];
+    __shared__ uint32_t s_mx[WARPS];
+    __shared__ int s_cnt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* lut = reinterpret_cast<uint16_t*>(smem_hist);            // SORTED: u16 byte offsets
     uint32_t* hist0 = smem_hist + (SORTED ? LUT_BYTES / 4 : 0);         // warp 0's histogram: the shared one of phase 1
@@ -394,11 +523,28 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
                     if (presence) presence[COLS] = 1u;                   // "some window holds a non-ACGT byte"
                 }
             }
-            flush_row<COLS, THREADS, TRACK>(hist0, out, threadIdx.x, pres1);
-            __syncthreads();
+            if constexpr (FUSE) {
+                const int32_t klen = fuse.key_len[row];
+                const double len = (double)klen;
+                unsigned long long sq = 0; uint32_t mx = 0;
+                flush_fused<COLS, THREADS>(hist0, threadIdx.x, row, fuse, len, 1.0 / len, sq, mx, pres1);
+                for (int o = 16; o > 0; o >>= 1) {
+                    sq += __shfl_xor_sync(FULL, sq, o);
+                    mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+                }
+                if (lane == 0) { s_sq[warp] = sq; s_mx[warp] = mx; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (int w = 1; w < WARPS; ++w) { sq += s_sq[w]; mx = max(mx, s_mx[w]); }
+                    write_rowmeta(fuse, row, sq, mx, klen);
+                }
+            } else {
+                flush_row<COLS, THREADS, TRACK>(hist0, out, threadIdx.x, pres1);
+                __syncthreads();
+            }
         }
     }
-    if constexpr (TRACK) publish_presence<COLS, THREADS>(presence, threadIdx.x, pres1);
+    if constexpr (TRACK && !FUSE) publish_presence<COLS, THREADS>(presence, threadIdx.x, pres1);
 
     // ================= phase 2: every warp on its own =================
     bool have_ticket = (warp == 0);                                      // the ticket that ended phase 1 is a class-2 ticket
@@ -414,6 +560,8 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
         const int nb = (int)((n - row0 < lp.batch) ? n - row0 : lp.batch);
         int64_t my_off = 0;
         if (lane <= nb) my_off = offsets[row0 + lane];                  // batch <= 31
+        int32_t my_len = 1;
+        if constexpr (FUSE) { if (lane < nb) my_len = fuse.key_len[row0 + lane]; }
         int64_t beg = __shfl_sync(FULL, my_off, 0);
         uint4 v = make_uint4(0, 0, 0, 0);
         bool have_v = false;                                             // v holds the first span of contig c
@@ -443,26 +591,54 @@ k1_count_warp(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
                     }
                 }
                 __syncwarp();
-                flush_row<COLS, 32, TRACK>(hist, counts + row * ld, lane, pres);
+                if constexpr (FUSE) {
+                    const int32_t klen = __shfl_sync(FULL, my_len, c);
+                    const double len = (double)klen;
+                    unsigned long long sq = 0; uint32_t mx = 0;
+                    flush_fused<COLS, 32>(hist, lane, row, fuse, len, 1.0 / len, sq, mx, pres);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sq += __shfl_xor_sync(FULL, sq, o);
+                        mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+                    }
+                    if (lane == 0) write_rowmeta(fuse, row, sq, mx, klen);
+                } else {
+                    flush_row<COLS, 32, TRACK>(hist, counts + row * ld, lane, pres);
+                }
                 __syncwarp();
                 have_v = A_after >= 0;
             }
             beg = end;
         }
     }
-    if constexpr (TRACK) publish_presence<COLS, 32>(presence, lane, pres);
+    if constexpr (TRACK && !FUSE) publish_presence<COLS, 32>(presence, lane, pres);
+    if constexpr (FUSE) {
+        // column presence of this CTA: both flush layouts -> bytes (the histograms are idle now) -> one store if complete
+        __syncthreads();
+        uint8_t* col = reinterpret_cast<uint8_t*>(hist0);
+        for (int c = threadIdx.x; c < COLS; c += THREADS) col[c] = 0;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        presence_to_bytes<COLS, THREADS>(col, threadIdx.x, pres1);
+        presence_to_bytes<COLS, 32>(col, lane, pres);
+        __syncthreads();
+        if (presence) publish_bytes<COLS>(col, presence, &s_cnt, threadIdx.x, THREADS);
+        if (blockIdx.x == 0) write_padding_rows(fuse, n, threadIdx.x, THREADS);
+    }
 }
 
 // ---- one CTA per contig (histograms of 16-64 KB)
-template <int KA, int KB, bool PALB, bool SORTED, int THREADS, bool TRACK>
+template <int KA, int KB, bool PALB, bool SORTED, int THREADS, bool TRACK, bool FUSE>
 __global__ void __launch_bounds__(THREADS)
 k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offsets, int64_t n,
              uint32_t* __restrict__ counts, int64_t ld, uint32_t* __restrict__ exotic_out,
-             uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp) {
+             uint32_t* __restrict__ presence, int32_t* scratch, LongPolicy lp, FuseOut fuse) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) uint32_t smem_hist[];
     __shared__ uint32_t s_red[NW];
+    __shared__ unsigned long long s_sq[NW];
+    __shared__ uint32_t s_mx[NW];
+    __shared__ int s_cnt;
     __shared__ int64_t s_row;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* lut = reinterpret_cast<uint16_t*>(smem_hist);
@@ -506,9 +682,37 @@ k1_count_cta(const uint8_t* __restrict__ bases, const int64_t* __restrict__ offs
                 if (presence) presence[COLS] = 1u;
             }
         }
-        flush_row<COLS, THREADS, TRACK>(hist, out, threadIdx.x, pres);
+        if constexpr (FUSE) {
+            const int32_t klen = fuse.key_len[row];
+            const double len = (double)klen;
+            unsigned long long sq = 0; uint32_t mx = 0;
+            flush_fused<COLS, THREADS>(hist, threadIdx.x, row, fuse, len, 1.0 / len, sq, mx, pres);
+            for (int o = 16; o > 0; o >>= 1) {
+                sq += __shfl_xor_sync(FULL, sq, o);
+                mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+            }
+            if (lane == 0) { s_sq[warp] = sq; s_mx[warp] = mx; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < NW; ++w) { sq += s_sq[w]; mx = max(mx, s_mx[w]); }
+                write_rowmeta(fuse, row, sq, mx, klen);
+            }
+        } else {
+            flush_row<COLS, THREADS, TRACK>(hist, out, threadIdx.x, pres);
+        }
     }
-    if constexpr (TRACK) publish_presence<COLS, THREADS>(presence, threadIdx.x, pres);
+    if constexpr (TRACK && !FUSE) publish_presence<COLS, THREADS>(presence, threadIdx.x, pres);
+    if constexpr (FUSE) {
+        __syncthreads();
+        uint8_t* col = reinterpret_cast<uint8_t*>(hist);
+        for (int c = threadIdx.x; c < COLS; c += THREADS) col[c] = 0;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        presence_to_bytes<COLS, THREADS>(col, threadIdx.x, pres);
+        __syncthreads();
+        if (presence) publish_bytes<COLS>(col, presence, &s_cnt, threadIdx.x, THREADS);
+        if (blockIdx.x == 0) write_padding_rows(fuse, n, threadIdx.x, THREADS);
+    }
 }
 
 // ---- split path: the flat list of chunks of all long contigs is dealt to the grid in contiguous ranges
@@ -583,7 +787,7 @@ k1_count_long(const uint8_t* __restrict__ bases, const int64_t* __restrict__ off
 
 template <int KA, int KB, bool PALB, bool SORTED>
 int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_t n,
-           uint32_t* d_counts, int64_t ld, uint32_t* d_exotic, uint32_t* d_presence, int track) {
+           uint32_t* d_counts, int64_t ld, uint32_t* d_exotic, uint32_t* d_presence, int track, const FuseOut* fuse) {
     constexpr int COLS = Bins<KA, KB, PALB>::TOTAL;
     constexpr bool WARP_PER_CONTIG = COLS <= 2048;
     constexpr int WARPS = 8;
@@ -599,13 +803,21 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
     KB_CUDA(cudaMemsetAsync(ctx->d_k1_scratch, 0, 8 * sizeof(int32_t), ctx->stream));
     const size_t smem_one = (size_t)(COLS + THREADS) * sizeof(uint32_t) + (SORTED ? LUT_BYTES : 0);   // histogram + dummy words (+ offset table)
     LongPolicy lp{4096, 1 << 16, 1 << 14, 4, 32};
-    const bool tr = track && d_presence;
+    const bool tr = track && d_presence && !fuse;
+    FuseOut fo;
+    memset(&fo, 0, sizeof(fo));
+    if (fuse) {
+        fo = *fuse;
+        lp.threshold = INT64_MAX;                                 // fused rows are never split: the longer contigs are binned by whole CTAs
+    }
     if constexpr (WARP_PER_CONTIG) {
         // 4 CTAs of 8 warps per SM (64 registers, no spills) beat 5 (48 registers): 0.088 vs 0.095 ms at 50k contigs
-        auto k1 = tr ? k1_count_warp<KA, KB, PALB, SORTED, WARPS, true, 4> : k1_count_warp<KA, KB, PALB, SORTED, WARPS, false, 4>;
+        // (the fused kernel: 0.141 ms with 4 CTAs per SM / 64 registers, 0.146 ms with 3 CTAs / 85 registers)
+        auto k1 = fuse ? k1_count_warp<KA, KB, PALB, SORTED, WARPS, false, 4, true>
+                       : (tr ? k1_count_warp<KA, KB, PALB, SORTED, WARPS, true, 4, false> : k1_count_warp<KA, KB, PALB, SORTED, WARPS, false, 4, false>);
         const size_t smem = (size_t)(COLS + 32) * sizeof(uint32_t) * WARPS + (SORTED ? LUT_BYTES : 0);
-        static int per_sm_cache[16][2] = {{0}};                // per device and variant: attribute set + occupancy known
-        int& per_sm = per_sm_cache[ctx->device & 15][tr ? 1 : 0];
+        static int per_sm_cache[16][3] = {{0}};                // per device and variant: attribute set + occupancy known
+        int& per_sm = per_sm_cache[ctx->device & 15][fuse ? 2 : (tr ? 1 : 0)];
         if (per_sm == 0) {
             KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, WARPS * 32, smem));
@@ -622,12 +834,13 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         if (grid < 1) grid = 1;
         KbTimer t(ctx, 0);
         k1<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                              d_presence, ctx->d_k1_scratch, lp);
+                                                              d_presence, ctx->d_k1_scratch, lp, fo);
         ctx->launches++;
     } else {
-        auto k1 = tr ? k1_count_cta<KA, KB, PALB, SORTED, THREADS, true> : k1_count_cta<KA, KB, PALB, SORTED, THREADS, false>;
-        static int per_sm_cache[16][2] = {{0}};
-        int& per_sm = per_sm_cache[ctx->device & 15][tr ? 1 : 0];
+        auto k1 = fuse ? k1_count_cta<KA, KB, PALB, SORTED, THREADS, false, true>
+                       : (tr ? k1_count_cta<KA, KB, PALB, SORTED, THREADS, true, false> : k1_count_cta<KA, KB, PALB, SORTED, THREADS, false, false>);
+        static int per_sm_cache[16][3] = {{0}};
+        int& per_sm = per_sm_cache[ctx->device & 15][fuse ? 2 : (tr ? 1 : 0)];
         if (per_sm == 0) {
             KB_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one));
             KB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, THREADS, smem_one));
@@ -636,14 +849,14 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
         int64_t grid = (int64_t)ctx->sm_count * per_sm;
         if (grid > n) grid = n;
         if (grid < 1) grid = 1;
-        if (n < 2 * (int64_t)ctx->sm_count * per_sm) lp = LongPolicy{16384, 16384, 8192, 1, 32};
+        if (!fuse && n < 2 * (int64_t)ctx->sm_count * per_sm) lp = LongPolicy{16384, 16384, 8192, 1, 32};
         KbTimer t(ctx, 0);
         k1<<<(unsigned)grid, THREADS, smem_one, ctx->stream>>>(d_bases, d_offsets, n, d_counts, ld, d_exotic,
-                                                               d_presence, ctx->d_k1_scratch, lp);
+                                                               d_presence, ctx->d_k1_scratch, lp, fo);
         ctx->launches++;
     }
     KB_CUDA(cudaGetLastError());
-    {
+    if (!fuse) {
         auto k1l = k1_count_long<KA, KB, PALB, SORTED, THREADS>;
         static bool attr_set[16] = {false};
         if (!attr_set[ctx->device & 15]) {
@@ -660,27 +873,64 @@ int launch(kb_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int64_
     return KB_OK;
 }
 
+template <class F>
+int dispatch_mode(const KbMode& m, F&& f) {
+    if (m.permute) return f(std::integral_constant<int, 0>{});     // kmer.py's sorted() column order
+    if (m.ka == 5 && m.kb == 6) return f(std::integral_constant<int, 1>{});
+    if (m.ka == 4 && m.kb == 5) return f(std::integral_constant<int, 2>{});
+    if (m.kb == 0) {
+        switch (m.ka) {
+            case 1: return f(std::integral_constant<int, 11>{});
+            case 2: return f(std::integral_constant<int, 12>{});
+            case 3: return f(std::integral_constant<int, 13>{});
+            case 4: return f(std::integral_constant<int, 14>{});
+            case 5: return f(std::integral_constant<int, 15>{});
+            case 6: return f(std::integral_constant<int, 16>{});
+            case 7: return f(std::integral_constant<int, 17>{});
+        }
+    }
+    kb_set_error("count mode not built");
+    return KB_EUNSUPPORTED;
+}
+
 }  // namespace
+
+static int launch_any(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases, const int64_t* d_offsets, int64_t n, uint32_t* d_counts,
+                      int64_t ld, uint32_t* d_exotic, uint32_t* d_presence, int track, const FuseOut* fuse) {
+#define KB_ARGS ctx, d_bases, d_offsets, n, d_counts, ld, d_exotic, d_presence, track, fuse
+    return dispatch_mode(m, [&](auto tag) -> int {
+        constexpr int T = decltype(tag)::value;
+        if constexpr (T == 0) return launch<5, 6, true, true>(KB_ARGS);
+        else if constexpr (T == 1) return launch<5, 6, false, false>(KB_ARGS);
+        else if constexpr (T == 2) return launch<4, 5, false, false>(KB_ARGS);
+        else return launch<T - 10, 0, false, false>(KB_ARGS);
+    });
+#undef KB_ARGS
+}
 
 int kb_launch_count_kernels(kb_ctx* ctx, const KbMode& m, const uint8_t* d_bases,
                             const int64_t* d_offsets, int64_t n, uint32_t* d_counts,
                             int64_t ld, uint32_t* d_exotic, uint32_t* d_presence, int track) {
-#define KB_ARGS ctx, d_bases, d_offsets, n, d_counts, ld, d_exotic, d_presence, track
-    if (m.permute) return launch<5, 6, true, true>(KB_ARGS);     // kmer.py's sorted() column order
-    if (m.ka == 5 && m.kb == 6) return launch<5, 6, false, false>(KB_ARGS);
-    if (m.ka == 4 && m.kb == 5) return launch<4, 5, false, false>(KB_ARGS);
-    if (m.kb == 0) {
-        switch (m.ka) {
-            case 1: return launch<1, 0, false, false>(KB_ARGS);
-            case 2: return launch<2, 0, false, false>(KB_ARGS);
-            case 3: return launch<3, 0, false, false>(KB_ARGS);
-            case 4: return launch<4, 0, false, false>(KB_ARGS);
-            case 5: return launch<5, 0, false, false>(KB_ARGS);
-            case 6: return launch<6, 0, false, false>(KB_ARGS);
-            case 7: return launch<7, 0, false, false>(KB_ARGS);
-        }
-    }
-#undef KB_ARGS
-    kb_set_error("count mode not built");
-    return KB_EUNSUPPORTED;
+    return launch_any(ctx, m, d_bases, d_offsets, n, d_counts, ld, d_exotic, d_presence, track, nullptr);
+}
+
+extern "C" int kb_count_profile(kb_ctx* ctx, int mode, const uint8_t* d_bases, const int64_t* d_offsets, const int32_t* d_key_len,
+                                int64_t n, int64_t n_alloc, double* d_profile, int64_t ld_profile, void* d_operand, int64_t ld_operand,
+                                kb_rowmeta* d_rowmeta, uint32_t* d_exotic, uint32_t* d_presence, uint32_t* d_flags_or) {
+    KB_CHECK_ARG(ctx && (n == 0 || (d_bases && d_offsets && d_key_len)), "null pointer");
+    KbMode m;
+    int rc = kb_mode_describe(mode, &m);
+    if (rc) return rc;
+    KB_CHECK_ARG(n >= 0 && n < (1LL << 31) - 2 && n_alloc >= n, "contig count");
+    KB_CHECK_ARG(((uintptr_t)d_bases % 16) == 0, "bases must be 16-byte aligned");
+    KB_CHECK_ARG(!d_profile || (ld_profile >= m.cols && ((uintptr_t)d_profile % 16) == 0), "profile ld/alignment");
+    KB_CHECK_ARG(!d_operand || (ld_operand >= m.cols && (ld_operand % 64) == 0 && ((uintptr_t)d_operand % 16) == 0),
+                 "operand ld must be a multiple of 64 and >= columns");
+    if (n_alloc == 0) return KB_OK;
+    KB_CUDA(cudaSetDevice(ctx->device));
+    FuseOut f;
+    f.key_len = d_key_len; f.profile = d_profile; f.ld_profile = ld_profile;
+    f.operand = reinterpret_cast<__half*>(d_operand); f.ld_operand = ld_operand;
+    f.rowmeta = d_rowmeta; f.flags_or = d_flags_or; f.n_alloc = n_alloc;
+    return launch_any(ctx, m, d_bases, d_offsets, n, nullptr, 0, d_exotic, d_presence, 0, &f);
 }

@@ -96,9 +96,9 @@ void build_sched(const KbKnnPlan& p, int64_t q_row0, int S, int kind, Sched* out
     for (int w = 0; w < W; ++w) { out->n_pieces += (int64_t)out->per_worker[w].size(); out->makespan = std::max(out->makespan, load[w]); }
 }
 
-// sync_only: the key set does not fit in L2, so concurrent workers must sweep the same key tiles at the same
-// time (whole bands dealt round-robin, at least 2 bands); otherwise every band may also be cut into equal ranges.
-void choose_sched(const KbKnnPlan& p, int64_t q_row0, int min_bands, bool sync_only, Sched* best, int* best_S, int* best_kind) {
+// min_bands[kind]: fewest key bands a schedule of that kind may use; sync_only: the key set is far beyond the L2, so
+// concurrent workers must sweep the same key tiles at the same time (whole bands dealt round-robin only).
+void choose_sched(const KbKnnPlan& p, int64_t q_row0, const int* min_bands, bool sync_only, Sched* best, int* best_S, int* best_kind) {
     static const int cand[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64};
     const int max_slots = KB_KNN_MAX_CAND / p.kp;
     bool have = false;
@@ -106,10 +106,10 @@ void choose_sched(const KbKnnPlan& p, int64_t q_row0, int min_bands, bool sync_o
     const char* fk = getenv("KB_KNN_SCHED");                             // experiments only: 0 round-robin units, 1 balanced cut
     for (int S : cand) {
         if (S > p.n_tiles || S > max_slots) break;
-        if (S < min_bands && S < p.n_tiles && S < max_slots) continue;
         if (fs && atoi(fs) >= 1 && S != std::min<int64_t>(std::min<int64_t>(atoi(fs), p.n_tiles), max_slots)) continue;
         for (int kind = 0; kind < 2; ++kind) {
             if (fk ? atoi(fk) != kind : (sync_only && kind == 1)) continue;
+            if (!fs && S < min_bands[kind] && S < p.n_tiles && S < max_slots) continue;
             Sched s;
             build_sched(p, q_row0, S, kind, &s);
             if (s.slots > max_slots) continue;
@@ -151,10 +151,16 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, 
             if (w > visits) w = visits;
             p->workers = (int)w;
             Sched s; int S = 1, kind = 0;
-            double l2_mb = 120.0;                                   // B200: 126 MB of L2
+            // B200: 126 MB of L2.  A key set that fills a good part of it is swept in bands that all workers share
+            // (measured in place, i.e. with the L2 cold after K1-K3: 50k x 1088 keys = 109 MB, one band cut into
+            // ranges 3.30 ms, three whole bands dealt round-robin 3.13 ms); beyond the L2 only whole bands are dealt.
+            double l2_mb = 120.0;
             if (const char* f = getenv("KB_KNN_L2_MB")) l2_mb = atof(f);   // experiments only
-            const bool sync_only = (double)nk * dp * 2.0 > l2_mb * 1e6;
-            const int min_bands = sync_only ? 2 : ((q_row0 > 0 || nq < nk) ? 4 : 1);
+            const double key_bytes = (double)nk * dp * 2.0;
+            const bool sync_only = key_bytes > l2_mb * 1e6;
+            const bool shard = q_row0 > 0 || nq < nk;                // arrival order: at least 4 bands
+            const int min_bands[2] = {key_bytes > 0.5 * l2_mb * 1e6 ? 2 : (shard ? 4 : 1),
+                                      (key_bytes > 0.5 * l2_mb * 1e6 || shard) ? 4 : 1};
             choose_sched(*p, q_row0, min_bands, sync_only, &s, &S, &kind);
             p->slots = s.slots; p->bands = S; p->sched_kind = kind; p->n_pieces = s.n_pieces; p->makespan = s.makespan;
         } else {

@@ -272,6 +272,25 @@ class Engine:
                                 ptr(exotic), ptr(presence)))
         return counts, exotic, presence
 
+    def count_profile(self, d_bases, d_offsets, d_key_len, lo, hi, mode, profile, operand, rowmeta, exotic, presence,
+                      flags_or, rows_alloc=None):
+        """K1+K3 fused (kb_count_profile) on rows [lo, hi) of preallocated outputs; the call that reaches the last
+        real row also writes the gather padding rows up to ``rows_alloc``."""
+        self._bind_stream()
+        n = d_offsets.numel() - 1
+        n_alloc = hi - lo
+        if rows_alloc is not None and hi == n:
+            n_alloc = int(rows_alloc) - lo
+        if n_alloc <= 0:
+            return
+        check(self.lib.kb_count_profile(self.ctx, mode, ptr(d_bases), ptr(d_offsets[lo:]), ptr(d_key_len[lo:]) if hi > lo else None,
+                                        hi - lo, n_alloc, ptr(profile[lo:]) if profile is not None and hi > lo else None,
+                                        profile.stride(0) if profile is not None else 0,
+                                        ptr(operand[lo:]) if operand is not None else None,
+                                        operand.stride(0) if operand is not None else 0,
+                                        ptr(rowmeta[lo:]), ptr(exotic[lo:]) if exotic is not None and hi > lo else None,
+                                        ptr(presence), ptr(flags_or)))
+
     def count_stats(self):
         nl, ex = c_int64(), c_int64()
         check(self.lib.kb_count_stats(self.ctx, byref(nl), byref(ex)))
@@ -478,25 +497,26 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
         for _, _, ev in chunks:
             main.wait_event(ev)
         chunks = None
-    counts = b.get("counts") if b.get("counts") is not None else torch.empty((n, cols_full), dtype=torch.int32, device=engine.device)
+    counts = None                                       # the optimistic pass never materialises the u32 count rows
+    if not optimistic:
+        counts = b.get("counts") if b.get("counts") is not None else torch.empty((n, cols_full), dtype=torch.int32, device=engine.device)
     exotic = b.get("exotic") if b.get("exotic") is not None else torch.empty(n, dtype=torch.int32, device=engine.device)
     presence = b.get("presence") if b.get("presence") is not None else torch.empty(cols_full + 1, dtype=torch.int32, device=engine.device)
     presence.zero_()
     d_or = torch.zeros(1, dtype=torch.int32, device=engine.device)
     profile = operand = rowmeta = None
     if optimistic:
-        # K1 leaves the column words to K3, which reads every row anyway
-        profile, operand, rowmeta = engine.normalise(counts, cols_full, d_key_len, want_profile=want_profile,
-                                                     want_operand=want_knn, rows_alloc=per, launch=False)
+        # K1+K3 fused: every contig's histogram goes straight to its profile / operand / record rows
+        rows = n if per is None else max(n, int(per))
+        profile = torch.empty((n, cols_full), dtype=torch.float64, device=engine.device) if want_profile else None
+        operand = torch.empty((rows, (cols_full + 63) // 64 * 64), dtype=torch.float16, device=engine.device) if want_knn else None
+        rowmeta = torch.empty((rows, 8), dtype=torch.int32, device=engine.device)
         for lo, hi, ev in (chunks or [(0, n, None)]):
             if ev is not None:
                 main.wait_event(ev)
-            if hi > lo:
-                engine.count(d_bases, d_offsets[lo:], hi - lo, mode, counts[lo:hi], exotic[lo:hi], presence,
-                             zero_presence=False, columns=False)
             if hi > lo or hi == n:
-                engine.normalise_rows(counts, cols_full, d_key_len, lo, hi, profile, operand, rowmeta,
-                                      rows_alloc=rowmeta.shape[0], presence=presence, flags_or=d_or)
+                engine.count_profile(d_bases, d_offsets[:n + 1], d_key_len, lo, hi, mode, profile, operand, rowmeta, exotic,
+                                     presence, d_or, rows_alloc=rowmeta.shape[0])
             if hi > lo and on_profile is not None and profile is not None:
                 on_profile(profile, lo, hi)
         columns = names
@@ -764,10 +784,9 @@ class PassPlan:
         self.d_bases = torch.zeros(cap, dtype=torch.uint8, device=dev)
         self.d_offsets = torch.zeros(self.n + 1, dtype=torch.int64, device=dev)
         self.d_key_len = torch.ones(max(self.n, 1), dtype=torch.int32, device=dev)
-        # K1 / K3 products
-        self.counts = torch.empty((self.n, self.cols), dtype=torch.int32, device=dev)
+        # K1 / K3 products (the u32 count rows are never materialised: kb_count_profile)
         self.exotic = torch.empty(max(self.n, 1), dtype=torch.int32, device=dev)
-        self.presence = torch.zeros(self.cols + 1, dtype=torch.int32, device=dev)
+        self.rec_words = self.cols + 1 + 4                      # per-rank record: [flags OR, uncertified rows, 0, 0, presence[0..D]]
         self.profile = torch.empty((self.n, self.cols), dtype=torch.float64, device=dev) if want_profile else None
         self.x = None
         self.side = None
@@ -778,10 +797,11 @@ class PassPlan:
             self.rowmeta_all = torch.empty((self.nk, 8), dtype=torch.int32, device=dev)
             self.all_idx = torch.empty((self.nk, k), dtype=torch.int32, device=dev) if self.want_knn else None
             self.all_dist = torch.empty((self.nk, k), dtype=torch.float32, device=dev) if self.want_knn else None
-            self.rec_all = torch.zeros((1, 4), dtype=torch.int32, device=dev)
+            self.rec_all = torch.zeros((1, self.rec_words), dtype=torch.int32, device=dev)
         self.idx = self.all_idx[self.q_row0:self.q_row0 + self.n] if self.want_knn else None
         self.dist = self.all_dist[self.q_row0:self.q_row0 + self.n] if self.want_knn else None
-        self.rec = self.rec_all[self.rank if self.x is not None else 0]      # [flags OR, uncertified rows, presence[D], 0]
+        self.rec = self.rec_all[self.rank if self.x is not None else 0]
+        self.presence = self.rec[4:]                             # K1/K3 write the presence vector straight into the record
         self.ws = None
         self._unc = None
         if self.want_knn:
@@ -792,7 +812,7 @@ class PassPlan:
                                                   ptr(self.ws), byref(out)))
             off = out.value - self.ws.data_ptr()
             self._unc = self.ws[off:off + 4].view(torch.int32)
-        self.h_val = [torch.zeros((self.rec_all.shape[0], 4), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.h_val = [torch.zeros(tuple(self.rec_all.shape), dtype=torch.int32).pin_memory() for _ in range(2)]
         self._events = [torch.cuda.Event(), torch.cuda.Event()]
         self._step = 0
         self.graph = None
@@ -806,7 +826,7 @@ class PassPlan:
         off = 1024
         lay = {}
         for name, nbytes in (("operand", W * per * dp * 2), ("rowmeta", W * per * 32), ("idx", W * per * k * 4),
-                             ("dist", W * per * k * 4), ("rec", W * 16)):
+                             ("dist", W * per * k * 4), ("rec", W * self.rec_words * 4)):
             lay[name] = off
             off = _round_up(off + nbytes, 256)
         self._lay, total = lay, off
@@ -836,7 +856,7 @@ class PassPlan:
         self.rowmeta_all = view("rowmeta", W * per * 32, torch.int32, (W * per, 8))
         self.all_idx = view("idx", W * per * k * 4, torch.int32, (W * per, k))
         self.all_dist = view("dist", W * per * k * 4, torch.float32, (W * per, k))
-        self.rec_all = view("rec", W * 16, torch.int32, (W, 4))
+        self.rec_all = view("rec", W * self.rec_words * 4, torch.int32, (W, self.rec_words))
         self.rec_all.zero_()
         # peers' gathered result arrays as seen from here (K5 stores its rows there)
         pi, pd = [], []
@@ -886,18 +906,14 @@ class PassPlan:
         main = torch.cuda.current_stream(e.device)
         if self.x is not None:
             check(lib.kb_xchg_begin(self.x))
-        self.presence.zero_()
-        self.rec.zero_()
-        if self.n:
-            check(lib.kb_count(e.ctx, self.mode | KB_COUNT_NO_COLUMNS, ptr(self.d_bases), ptr(self.d_offsets), self.n,
-                               ptr(self.counts), self.counts.stride(0), ptr(self.exotic), ptr(self.presence)))
+        self.rec.zero_()                                        # flags, uncertified rows and the presence vector
         n_alloc = self.per if self.x is not None else self.n
         lo = self.q_row0
-        check(lib.kb_normalise(e.ctx, ptr(self.counts) if self.n else None, self.counts.stride(0), self.cols,
-                               ptr(self.d_key_len) if self.n else None, self.n, n_alloc,
-                               ptr(self.profile) if self.profile is not None and self.n else None, self.cols,
-                               ptr(self.operand_all[lo:]) if self.want_knn else None, self.dp,
-                               ptr(self.rowmeta_all[lo:]), ptr(self.presence), ptr(self.rec)))
+        # K1+K3 fused: the histogram of every contig goes straight to its profile / operand / record rows
+        check(lib.kb_count_profile(e.ctx, self.mode, ptr(self.d_bases), ptr(self.d_offsets), ptr(self.d_key_len), self.n, n_alloc,
+                                   ptr(self.profile) if self.profile is not None and self.n else None, self.cols,
+                                   ptr(self.operand_all[lo:]) if self.want_knn else None, self.dp,
+                                   ptr(self.rowmeta_all[lo:]), ptr(self.exotic), ptr(self.presence), ptr(self.rec)))
         if self.x is not None:
             ev = torch.cuda.Event()
             ev.record(main)
@@ -908,9 +924,8 @@ class PassPlan:
                              self.nk, self.q_row0, self.n, None, None, 0, 0, 0, ptr(self.idx), ptr(self.dist), None,
                              ptr(self.ws), self.ws.numel(), byref(self._xchg) if self.x is not None else None))
             self.rec[1:2].copy_(self._unc, non_blocking=True)
-        self.rec[2:3].copy_(self.presence[self.cols:], non_blocking=True)
         if self.x is not None:
-            check(lib.kb_xchg_finish(self.x, self._lay["rec"], 4))
+            check(lib.kb_xchg_finish(self.x, self._lay["rec"], self.rec_words))
             main.wait_stream(self.side)
 
     def capture(self, warmup=2):
@@ -953,10 +968,8 @@ class PassPlan:
         v = self.h_val[slot].numpy()
         flags_or = int(np.bitwise_or.reduce(v[:, 0]))
         unc = int(v[:, 1].sum())
-        last = int(np.bitwise_or.reduce(v[:, 2] & 1)) | (2 if (v[:, 2] & 2).any() else 0)
-        exo, complete = bool(last & 1), bool(last & 2)
-        if not complete and not self.multi:
-            complete = bool(self.presence[:-1].cpu().numpy().all())
+        pres = np.bitwise_or.reduce(v[:, 4:], axis=0)            # OR over the ranks: column words, [D] = exotic | complete bits
+        exo, complete = _presence_summary(pres, self.faithful)
         ok = not exo and (complete or not self.faithful) and not (self.want_knn and (flags_or & 3)) and not (flags_or & 4)
         return {"ok": ok, "flags_or": flags_or, "uncertified": unc, "exotic": exo, "complete": complete}
 

@@ -144,3 +144,41 @@ def _slice(asm, rows):
     off = np.zeros(len(rows) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     return np.concatenate(seqs), off
+
+
+@pytest.mark.parametrize("mode", ["5p6", "5+6", "4+5", 1, 3, 5, 6, 7])
+def test_fused_count_profile_equals_count_then_normalise(engine, mode):
+    """kb_count_profile (K1+K3 in one kernel, no u32 rows in HBM) against kb_count + kb_normalise: profile, operand and
+    row records bit for bit, incl. empty / short / 70 kb / 200 kb contigs (no split path in the fused kernel), padding
+    rows, the exotic tallies and the presence summary."""
+    rng = np.random.default_rng(13)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    seqs = [rnd(int(x)) for x in rng.integers(200, 6000, 300)] + ["", "ACG", rnd(70000), rnd(200001), "A" * 5000, rnd(4096), rnd(4097),
+                                                                  rnd(300) + "N" + rnd(200), "acgt" + rnd(50)]
+    bases, offsets = _pack(seqs)
+    n = len(seqs)
+    key_len = rng.integers(3, 60, n).astype(np.int32)
+    m = mode_of(mode)
+    d_bases, d_offsets, d_len = engine.upload(bases, offsets, key_len)
+    counts, exotic, presence = engine.count(d_bases, d_offsets, n, m)
+    cols = counts.shape[1]
+    flags_a = torch.zeros(1, dtype=torch.int32, device="cuda")
+    prof_a, op_a, meta_a = engine.normalise(counts, cols, d_len, rows_alloc=n + 3, flags_or=flags_a)
+    prof_b = torch.empty_like(prof_a); op_b = torch.full_like(op_a, 7.0); meta_b = torch.full_like(meta_a, -5)
+    exo_b = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    pres_b = torch.zeros(cols + 1, dtype=torch.int32, device="cuda")
+    flags_b = torch.zeros(1, dtype=torch.int32, device="cuda")
+    engine.count_profile(d_bases, d_offsets, d_len, 0, n, m, prof_b, op_b, meta_b, exo_b, pres_b, flags_b, rows_alloc=n + 3)
+    torch.cuda.synchronize()
+    assert torch.equal(prof_a.view(torch.int64), prof_b.view(torch.int64)), "profile rows differ"
+    assert torch.equal(op_a.view(torch.int16), op_b.view(torch.int16)), "operand rows differ"
+    assert torch.equal(meta_a, meta_b), "row records differ"
+    assert torch.equal(exotic, exo_b) and int(flags_a) == int(flags_b)
+    pa, pb = presence.cpu().numpy(), pres_b.cpu().numpy()
+    assert (pa[-1] != 0) == bool(pb[-1] & 1)
+    complete = bool(pb[-1] & 2) or bool((pb[:-1] != 0).all())
+    assert complete == bool((pa[:-1] != 0).all())
+    if not (pb[-1] & 2):
+        assert np.array_equal(pa[:-1] != 0, pb[:-1] != 0)
