@@ -349,7 +349,16 @@ def big_run(torch, dist, eng, a, n_total, rank, world, local, pk):
         norm_ms, _ = eng.stage_ms("normalise")
         rerank_ms, _ = eng.stage_ms("rerank")
         eng.enable_timing(False)
-        # host to host: pinned inputs up, profile shard + this rank's lists down
+        if any(not c["ok"] for c in checks + [first]):
+            raise RuntimeError("optimistic validation failed on the synthetic shard: %r" % (checks,))
+        # rows K5 could not certify are redone exactly (all ranks take part: the count is the sum over ranks)
+        unc = checks[-1]["uncertified"]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fixed = plan.fixup() if unc else 0
+        torch.cuda.synchronize()
+        fix_s = time.perf_counter() - t0
+        # host to host: pinned inputs up, profile shard + this rank's lists down, uncertified rows redone
         h_prof = torch.empty(tuple(plan.profile.shape), dtype=torch.float64).pin_memory()
         h_idx = torch.empty(tuple(plan.idx.shape), dtype=torch.int32).pin_memory()
         h_dst = torch.empty(tuple(plan.dist.shape), dtype=torch.float32).pin_memory()
@@ -360,24 +369,25 @@ def big_run(torch, dist, eng, a, n_total, rank, world, local, pk):
         plan.load(h_bases, h_off, h_len)
         tok = plan.run()
         h_prof.copy_(plan.profile, non_blocking=True)
+        last = plan.check(tok)
+        if last["uncertified"]:
+            plan.fixup()
         h_idx.copy_(plan.idx, non_blocking=True)
         h_dst.copy_(plan.dist, non_blocking=True)
-        last = plan.check(tok)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         e2e_s = time.perf_counter() - t0
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([e2e_s, fix_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-        unc = sum(c["uncertified"] for c in checks[-1:])
-        if any(not c["ok"] for c in checks + [first, last]):
-            raise RuntimeError("optimistic validation failed on the synthetic shard: %r" % (checks,))
-        fixed = plan.fixup() if unc else 0                      # collective decision: `uncertified` is the sum over ranks
+        e2e_s, fix_s = float(tt[0].item()), float(tt[1].item())
+        if not last["ok"]:
+            raise RuntimeError("optimistic validation failed on the synthetic shard: %r" % (last,))
         rec = None
         if rank == 0:
             # parity sample: rows of rank 0 against ALL keys, truth from the gathered integer counts
+            blas_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
             rows = np.unique(np.linspace(0, shard.n - 1, 128).astype(np.int64))
             meta = plan.rowmeta_all.cpu().numpy()
             real = (meta[:, 3] & 8) == 0
@@ -400,7 +410,8 @@ def big_run(torch, dist, eng, a, n_total, rank, world, local, pk):
             flops = 2.0 * shard.n * float(n_total) * plan.cols
             tf = flops / (gemm_ms / 1e3) / 1e12
             rec = {"workload": "%d-contig S1 assembly, -k 5+6 (5120 dense columns), n_neighbors=15, %d GPUs, shards synthesised per rank" % (n_total, world),
-                   "ms_per_step": ms / 2, "contigs_per_s": n_total * 2 / (ms / 1e3), "steps": 2,
+                   "ms_per_step": ms / 2 + fix_s * 1e3, "contigs_per_s": n_total / (ms / 2e3 + fix_s), "steps": 2,
+                   "pass_ms": ms / 2, "exact_redo_ms": fix_s * 1e3,
                    "e2e_ms_per_step": e2e_s * 1e3, "e2e_contigs_per_s": n_total / e2e_s,
                    "e2e_bytes": {"h2d": int(h_bases.numel() + h_off.numel() * 8 + h_len.numel() * 4),
                                  "d2h": int(h_prof.numel() * 8 + h_idx.numel() * 8)},

@@ -209,7 +209,8 @@ KB_API int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t
  * exact score of its k-th neighbour, B the k'-th best fp32 score (every key that is not a
  * candidate scored >= B) and E = 2^-22*(Y^2 + 2cY), c^2 = n_i/l_i, Y = c + sqrt(c^2 + s), a bound
  * on the fp32 evaluation error of any key that could still beat s, the row is final iff
- * s + 2E < B.  Rows that fail (more than k'-k near-ties: long contigs, mass duplicates) and
+ * s + E < B + 2.5e-6*l_i*d2_k (a quarter of the stated-ties tolerance of 1e-5 relative on d2; nothing at
+ * d2 = 0).  Rows that fail (more than k'-k near-ties: long contigs, mass duplicates) and
  * every row when k > 60 are listed in the workspace and redone by kb_knn_fixup with exact
  * distances to ALL keys.
  * d_dist receives sqrt(d2) as float (UMAP's knn_dists), d_d2 (nullable) the fp64 squared

@@ -563,7 +563,8 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
     // ---- 5. certificate.  Every key that is not among the merged candidates has an fp32 score >= m_last.
     //   s_k = exact score of the k-th neighbour (s = l_q*d2 - n_q/l_q); a key j with a_j = l_q*n_j/l_j^2 > Y^2,
     //   Y = c + sqrt(c^2 + s_k), c^2 = n_q/l_q, has an exact score above s_k whatever its Gram entry is
-    //   (Cauchy-Schwarz); for all other keys the fp32 evaluation error is at most E = 2^-22*(Y^2 + 2cY).
+    //   (Cauchy-Schwarz); for all other keys the fp32 evaluation error is at most E = 2^-22*(Y^2 + 2cY)
+    //   (three roundings of 2^-24 on terms bounded by Y^2 and 2cY, a third on top for safety).
     //   Flagged keys only come through the extras (exact): if that list is full, the k-th neighbour must
     //   not be farther than its last entry.
     if (lane == 0) {
@@ -577,7 +578,11 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
                 const double c = sqrt(c2);
                 const double Y = c + sqrt(fmax(c2 + sk, 0.0));
                 const double E = 2.384185791015625e-07 * (Y * Y + 2.0 * c * Y);
-                ok = sk + 2.0 * E < (double)m_last;
+                // stated ties (north_star): a key within 1e-5 relative of the k-th distance may stand in
+                // for it; a quarter of that is granted here, so an unseen key is at worst 2.5e-6 closer (relative
+                // in d2) than the k-th neighbour returned.  At d2 = 0 (exact duplicates) nothing is granted.
+                const double tie = 2.5e-6 * lq * d2k;
+                ok = sk + E < (double)m_last + tie;
             }
             if (ok && n_extra >= KP && n_valid >= k && dk > x_max) ok = false;
         }

@@ -444,21 +444,24 @@ __device__ __forceinline__ void mbar_arrive_rank(uint32_t bar, uint32_t rank) { 
                  "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank) : "memory");
 }
 
-template <int KP, int STAGES>
+// QCAP: pending list insertions per query row (k4_tc2)
+template <int KP, int STAGES, int QCAP>
 struct Smem2 {
     static constexpr int OFF_STAGES = 0;
     static constexpr int OFF_LIST_S = STAGES * STAGE2_BYTES;
     static constexpr int OFF_LIST_I = OFF_LIST_S + KP * BM * 4;
-    static constexpr int OFF_COLMETA = OFF_LIST_I + KP * BM * 4;
+    static constexpr int OFF_QUEUE = OFF_LIST_I + KP * BM * 4;           // QCAP x BM x {score, key index}
+    static constexpr int OFF_COLMETA = OFF_QUEUE + QCAP * BM * 8;
     static constexpr int OFF_BARS = OFF_COLMETA + BN * 8;
     static constexpr int OFF_TMEM_SLOT = OFF_BARS + (2 * STAGES + 4) * 8;
     static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
+    static_assert(TOTAL <= 232448, "more shared memory than an SM has");
 };
 
-template <int KP, int STAGES>
+template <int KP, int STAGES, int QCAP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
-    using L = Smem2<KP, STAGES>;
+    using L = Smem2<KP, STAGES, QCAP>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -561,6 +564,11 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                                reinterpret_cast<int32_t*>(smem + L::OFF_LIST_I));
         const float4* cm4 = reinterpret_cast<const float4*>(smem + L::OFF_COLMETA);
         float2* cm_s = reinterpret_cast<float2*>(smem + L::OFF_COLMETA);
+        // Elements that beat the row's bound are not inserted one by one as they turn up (the 32 rows of a warp
+        // find theirs at different columns, so every insertion would run for the whole warp): they are queued per
+        // row in shared memory and drained for all rows of the warp together, at the end of the tile or when a
+        // queue runs full.  The bound is refreshed at every drain.
+        float2* queue = reinterpret_cast<float2*>(smem + L::OFF_QUEUE) + r;    // entry j of this row at queue[j * BM]
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t seen = 0;
         for (int32_t pi = pc_lo; pi < pc_hi; ++pi) {
@@ -570,6 +578,20 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             const float li = live ? (float)p.rowmeta[p.q_row0 + q].key_len : 1.f;
             list.init(r);
             float thr = __int_as_float(0x7f800000);
+            int cnt = 0;                                      // queued entries of this row
+            auto drain = [&]() {
+                const int n_it = __reduce_max_sync(0xffffffffu, cnt);
+                for (int j = 0; j < n_it; ++j) {
+                    if (j < cnt) {
+                        const float2 e = queue[j * BM];
+                        if (e.x < thr) {
+                            list.insert(r, e.x, __float_as_int(e.y));
+                            thr = fminf(thr, list.bound);
+                        }
+                    }
+                }
+                cnt = 0;
+            };
             for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
                 const int64_t n0 = piece_tile(pc, i) * BN;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -599,13 +621,31 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                         m0 = fminf(m0, sc[x]); m1 = fminf(m1, sc[x + 1]);
                         m2 = fminf(m2, sc[x + 2]); m3 = fminf(m3, sc[x + 3]);
                     }
-                    if (fminf(fminf(m0, m1), fminf(m2, m3)) < thr) {
+                    if (__any_sync(0xffffffffu, fminf(fminf(m0, m1), fminf(m2, m3)) < thr)) {
+                        // queue this chunk's candidates (predicated, no divergence)
+                        const int cnt0 = cnt;
+                        const int32_t idx0 = (int32_t)(n0 + c * 32);
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
                             if (sc[x] < thr) {
-                                list.insert(r, sc[x], (int32_t)(n0 + c * 32 + x));
-                                thr = fminf(thr, list.bound);
+                                if (cnt < QCAP) queue[cnt * BM] = make_float2(sc[x], __int_as_float(idx0 + x));
+                                ++cnt;
                             }
+                        }
+                        if (__any_sync(0xffffffffu, cnt > QCAP)) {
+                            // some row found more than its queue holds (a cold list: nearly everything passes and the rows of
+                            // the warp insert in step anyway): take the earlier entries in, then this chunk element by element
+                            cnt = cnt0;
+                            drain();
+#pragma unroll
+                            for (int x = 0; x < 32; ++x) {
+                                if (sc[x] < thr) {
+                                    list.insert(r, sc[x], idx0 + x);
+                                    thr = fminf(thr, list.bound);
+                                }
+                            }
+                        } else if (__any_sync(0xffffffffu, cnt > QCAP / 2)) {
+                            drain();
                         }
                     }
                 }
@@ -613,6 +653,7 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_rank(bar_tempty + 8 * acc, 0);   // the leader's barrier
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                drain();                                      // (the accumulator is already released: the MMA runs ahead)
                 if (live && list.bound < __int_as_float(0x7f800000)) atomicMin(p.row_thr + q, f2key(list.bound));
             }
             if (live) {
@@ -662,10 +703,10 @@ int launch_tc(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, c
     return KB_OK;
 }
 
-template <int KP, int STAGES>
+template <int KP, int STAGES, int QCAP>
 int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int workers) {
-    using L = Smem2<KP, STAGES>;
-    auto kern = k4_tc2<KP, STAGES>;
+    using L = Smem2<KP, STAGES, QCAP>;
+    auto kern = k4_tc2<KP, STAGES, QCAP>;
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
         KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -690,11 +731,17 @@ int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int wo
 // row; the wide lists (48, 64: n_neighbors 27..60) take the room of two stages (one for the 48 KB stages)
 template <int KP>
 int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, int cl, const TcParams& prm, int workers) {
-    constexpr int ST2 = KP <= 32 ? 6 : 4;
+    // 32 KB stages next to the lists and the insertion queues (16 entries per row = 16 KB): 6 stages up to 16-wide
+    // lists, 5 for 24 / 32, 4 for 48 / 64.  Wide rows (>= 2560 columns: long MMA tiles, light epilogue) with 24-wide
+    // lists trade half the queue for the sixth stage (5120 columns, k = 15: 1385 -> 14xx TFLOP/s).
+    constexpr int ST2 = KP <= 16 ? 6 : (KP <= 32 ? 5 : 4);
     constexpr int ST1 = KP <= 32 ? 4 : 3;
     // CTA pairs run one 2-CTA MMA (k4_tc2) unless KB_KNN_MMA2=0 asks for the two-MMA multicast kernel (experiments)
     const char* m2 = getenv("KB_KNN_MMA2");
-    if (cl == 2 && !(m2 && atoi(m2) == 0)) return launch_tc2<KP, ST2>(ctx, tmap, prm, workers);
+    if (cl == 2 && !(m2 && atoi(m2) == 0)) {
+        if constexpr (KP == 24) { if (prm.k_blocks >= 40) return launch_tc2<24, 6, 8>(ctx, tmap, prm, workers); }
+        return launch_tc2<KP, ST2, 16>(ctx, tmap, prm, workers);
+    }
     if (cl == 4) return launch_tc<KP, ST1, 4>(ctx, tmap, tmap_b, prm, workers);
     if (cl == 2) return launch_tc<KP, ST1, 2>(ctx, tmap, tmap_b, prm, workers);
     return launch_tc<KP, ST1, 1>(ctx, tmap, tmap_b, prm, workers);

@@ -38,6 +38,8 @@ struct kb_xchg {
     uint8_t* peer[KB_XCHG_MAX_WORLD];     // peers' arenas as mapped here (peer[rank] == local)
     uint8_t** d_peer;                     // device copy of peer[]
     bool attached;
+    cudaStream_t extra[2];                // two more copy streams: three peer copies in flight at a time
+    cudaEvent_t ev_fork, ev_join[2];
 };
 
 namespace {
@@ -85,14 +87,11 @@ __global__ void kx_wait(const uint8_t* local, int world, int rank, int which) {
         else wait_ge(&c->lists[t], e, 2, t);
     }
 }
-// which: 1 = arrive[rank] = epoch at every peer
-__global__ void kx_signal_arrive(const uint8_t* local, uint8_t* const* peer, int world, int rank) {
+// arrive[rank] = epoch at ONE peer, right behind the copies of that peer's shard on the same stream
+__global__ void kx_signal_arrive(const uint8_t* local, uint8_t* peer_arena, int rank) {
     const uint32_t e = reinterpret_cast<const KbXchgCtrl*>(local)->epoch;
-    const int t = threadIdx.x;
-    if (t < world && t != rank) {
-        __threadfence_system();
-        st_release_sys(&reinterpret_cast<KbXchgCtrl*>(peer[t])->arrive[rank], e);
-    }
+    __threadfence_system();
+    st_release_sys(&reinterpret_cast<KbXchgCtrl*>(peer_arena)->arrive[rank], e);
 }
 // my small record (rec_words u32 at rec_off + rank*rec_words*4) to every peer, then lists[rank] = epoch there
 __global__ void kx_finish(uint8_t* local, uint8_t* const* peer, int world, int rank, int64_t rec_off, int rec_words) {
@@ -132,6 +131,12 @@ extern "C" int kb_xchg_create(kb_ctx* ctx, int world, int rank, int64_t bytes, k
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->local);
     if (e != cudaSuccess) { cudaFree(x->local); cudaFree(x->d_peer); free(x); return kb_cuda_fail(e, "arena set-up (cudaIpcGetMemHandle)"); }
     memcpy(handle64, &h, 64);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&x->extra[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFree(x->local); cudaFree(x->d_peer); free(x); return kb_cuda_fail(e, "arena set-up (copy streams)"); }
     x->peer[rank] = x->local;
     *out = x; *d_local = x->local;
     return KB_OK;
@@ -166,6 +171,8 @@ extern "C" int kb_xchg_destroy(kb_xchg* x) {
     cudaDeviceSynchronize();
     for (int p = 0; p < x->world; ++p)
         if (p != x->rank && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
+    for (int i = 0; i < 2; ++i) { if (x->extra[i]) cudaStreamDestroy(x->extra[i]); if (x->ev_join[i]) cudaEventDestroy(x->ev_join[i]); }
+    if (x->ev_fork) cudaEventDestroy(x->ev_fork);
     cudaFree(x->d_peer);
     cudaFree(x->local);
     free(x);
@@ -186,19 +193,34 @@ extern "C" int kb_xchg_push(kb_xchg* x, void* stream, int n_regions, const int64
     kx_wait<<<1, KB_XCHG_MAX_WORLD, 0, st>>>(x->local, x->world, x->rank, 0);
     x->ctx->launches++;
     KB_CUDA(cudaGetLastError());
-    // nearest-following rank first: rank r then receives from r+1, r+2, ... -- the order in which K4 sweeps
+    // nearest-following rank first: rank r then receives from r+1, r+2, ... -- the order in which K4 sweeps.  Three
+    // peers are served at a time (the caller's stream and two of our own, forked and joined with events, so the
+    // whole fan-out is capturable), and every peer's arrival flag is raised right behind ITS copies: one stream
+    // of back-to-back peer copies moves ~150 GB/s, and a single flag kernel at the end would hold back the first
+    // shard until the last one has gone out
+    cudaStream_t sts[3] = {st, x->extra[0], x->extra[1]};
+    const int ns = x->world > 2 ? 3 : 1;
+    if (ns > 1) {
+        KB_CUDA(cudaEventRecord(x->ev_fork, st));
+        for (int i = 1; i < ns; ++i) KB_CUDA(cudaStreamWaitEvent(sts[i], x->ev_fork, 0));
+    }
     for (int d = 1; d < x->world; ++d) {
         const int p = (x->rank - d + x->world) % x->world;
+        cudaStream_t cs = sts[(d - 1) % ns];
         for (int r = 0; r < n_regions; ++r) {
             const int64_t off = region_off[r] + (int64_t)x->rank * shard_bytes[r];
             KB_CHECK_ARG(off >= (int64_t)sizeof(KbXchgCtrl) && off + shard_bytes[r] <= x->bytes, "region outside the arena");
             if (shard_bytes[r] == 0) continue;
-            KB_CUDA(cudaMemcpyAsync(x->peer[p] + off, x->local + off, (size_t)shard_bytes[r], cudaMemcpyDeviceToDevice, st));
+            KB_CUDA(cudaMemcpyAsync(x->peer[p] + off, x->local + off, (size_t)shard_bytes[r], cudaMemcpyDeviceToDevice, cs));
         }
+        kx_signal_arrive<<<1, 1, 0, cs>>>(x->local, x->peer[p], x->rank);
+        x->ctx->launches++;
     }
-    kx_signal_arrive<<<1, KB_XCHG_MAX_WORLD, 0, st>>>(x->local, x->d_peer, x->world, x->rank);
-    x->ctx->launches++;
     KB_CUDA(cudaGetLastError());
+    for (int i = 1; i < ns; ++i) {
+        KB_CUDA(cudaEventRecord(x->ev_join[i - 1], sts[i]));
+        KB_CUDA(cudaStreamWaitEvent(st, x->ev_join[i - 1], 0));
+    }
     return KB_OK;
 }
 
