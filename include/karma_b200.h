@@ -66,7 +66,8 @@ typedef struct kb_rowmeta {
  *                    the north-star throughput shape, NOT kmer.py's columns.
  *  KB_MODE_DENSE_4_5 256 + 1024 = 1280 columns.
  *  KB_MODE_K(k)      integer k (kmer.py:83-85), 4^k columns in code order
- *                    (== sorted() order for ACGT), 1 <= k <= 7.
+ *                    (== sorted() order for ACGT), 1 <= k <= 7; k = 8..16 through
+ *                    kb_kmer_sorted_collect (columns = the observed k-mers).
  * Codes are base-4 big-endian with A=0 C=1 G=2 T=3 (uppercase only: kmer.py
  * has no alphabet, any other byte makes an "exotic" window, see kb_count). */
 #define KB_MODE_5P6        0
@@ -146,6 +147,17 @@ KB_API int kb_exotic_fetch(kb_ctx* ctx, uint64_t* h_keys,
  *  d_key_col int32[n_keys] destination column of each unique key. */
 KB_API int kb_exotic_scatter(kb_ctx* ctx, const int32_t* d_key_col,
                       uint32_t* d_counts, int64_t ld);
+
+/* ---- integer k >= 8: sorted k-mer counting ---------------------------------------------
+ * kmer.py:83-85 accepts any integer -k; beyond k = 7 the 4^k bins leave shared memory, and kmer.py's columns are
+ * the OBSERVED k-mers anyway (kmer.py:146-179).  kb_kmer_sorted_collect turns every k-window of every contig,
+ * whatever bytes it holds, into a 128-bit key (8 bits per character, big-endian; 1 <= k <= 16), sorts, and
+ * reduces to the unique keys (ascending == Python sorted() order) and the (row, key, count) entries, on the GPU.
+ * Synchronises.  kb_kmer_sorted_fetch copies the unique keys out (hi = characters 0..7, lo = 8..15);
+ * kb_exotic_scatter then writes the counts into a zeroed matrix (d_key_col: destination column of each key). */
+KB_API int kb_kmer_sorted_collect(kb_ctx* ctx, int k, const uint8_t* d_bases, const int64_t* d_offsets, int64_t n,
+                           int64_t* n_keys, int64_t* n_entries);
+KB_API int kb_kmer_sorted_fetch(kb_ctx* ctx, uint64_t* h_keys_hi, uint64_t* h_keys_lo);
 
 /* ---- K2: column compaction -------------------------------------------------
  * Replaces the sorted(set) column dictionary of __extract_kmers

@@ -44,6 +44,8 @@ SIGNATURES = {
     "kb_exotic_collect": (c_int, [_P, c_int, _P, _P, c_int64, _P, POINTER(c_int64), POINTER(c_int64)]),
     "kb_exotic_fetch": (c_int, [_P, _P, _P, _P, _P]),
     "kb_exotic_scatter": (c_int, [_P, _P, _P, c_int64]),
+    "kb_kmer_sorted_collect": (c_int, [_P, c_int, _P, _P, c_int64, POINTER(c_int64), POINTER(c_int64)]),
+    "kb_kmer_sorted_fetch": (c_int, [_P, _P, _P]),
     "kb_compact": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32]),
     "kb_normalise": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P]),
     "kb_count_profile": (c_int, [_P, c_int, _P, _P, _P, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, _P]),

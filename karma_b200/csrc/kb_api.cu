@@ -71,8 +71,8 @@ extern "C" int kb_create(kb_ctx** out, int device) {
 }
 
 static void kb_free_exotic(kb_ctx* c) {
-    cudaFree(c->d_ex_keys); cudaFree(c->d_ex_row); cudaFree(c->d_ex_keyidx); cudaFree(c->d_ex_cnt);
-    c->d_ex_keys = nullptr; c->d_ex_row = nullptr; c->d_ex_keyidx = nullptr; c->d_ex_cnt = nullptr;
+    cudaFree(c->d_ex_keys); cudaFree(c->d_ex_keys_hi); cudaFree(c->d_ex_row); cudaFree(c->d_ex_keyidx); cudaFree(c->d_ex_cnt);
+    c->d_ex_keys = nullptr; c->d_ex_keys_hi = nullptr; c->d_ex_row = nullptr; c->d_ex_keyidx = nullptr; c->d_ex_cnt = nullptr;
     c->ex_n_keys = c->ex_n_entries = 0;
 }
 

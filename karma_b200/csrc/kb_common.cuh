@@ -25,7 +25,8 @@ struct kb_ctx {
     int32_t* d_k1_scratch;          // [0] contig counter, [1] n_long, [2..] long ids
     int64_t k1_scratch_cap;         // capacity in int32 entries
     // exotic side path (owned)
-    uint64_t* d_ex_keys;            // unique keys
+    uint64_t* d_ex_keys;            // unique keys (sorted k-mer path: the low 8 characters)
+    uint64_t* d_ex_keys_hi;         // sorted k-mer path (k >= 8): the first 8 characters of every unique key
     int32_t* d_ex_row; int32_t* d_ex_keyidx; uint32_t* d_ex_cnt;
     int64_t ex_n_keys, ex_n_entries;
     // read-graph edges of the last kb_readgraph_build (owned)

@@ -22,6 +22,11 @@ from ._lib import (KB_COUNT_NO_COLUMNS, KB_KNN_AUTO, KB_MODE_5P6, KB_MODE_DENSE_
                    check, ptr)
 
 _BASES = "ACGT"
+SORTED_K_MIN, SORTED_K_MAX = 8, 16          # integer k of the sorted counting path (kb_kmer_sorted_collect)
+
+
+def is_sorted_mode(mode):
+    return mode >= KB_MODE_K(SORTED_K_MIN)
 
 
 def mode_of(kmer_size):
@@ -33,8 +38,10 @@ def mode_of(kmer_size):
     if kmer_size == "4+5":
         return KB_MODE_DENSE_4_5
     if isinstance(kmer_size, (int, np.integer)) and not isinstance(kmer_size, bool):
-        if not 1 <= int(kmer_size) <= 7:
-            raise _lib.KarmaB200Error(-4, "integer k-mer sizes 1..7 are built (got %r)" % (kmer_size,))
+        # k <= 7: dense shared-memory histograms over the ACGT code space; 8 <= k <= 16: sorted k-mer keys
+        # (columns = the observed k-mers, as in kmer.py).  Beyond 16 a k-mer no longer fits the 128-bit sort key.
+        if not 1 <= int(kmer_size) <= SORTED_K_MAX:
+            raise _lib.KarmaB200Error(-4, "integer k-mer sizes 1..%d are built (got %r)" % (SORTED_K_MAX, kmer_size))
         return KB_MODE_K(int(kmer_size))
     # same failure kmer.py produces for e.g. "4p5": len(seq) - "4p5" -> TypeError (kmer.py:84)
     raise TypeError("unsupported operand type(s) for -: 'int' and %r" % type(kmer_size).__name__)
@@ -344,6 +351,39 @@ class Engine:
             check(self.lib.kb_exotic_scatter(self.ctx, ptr(d_keycol), ptr(out), ld_out))
         return columns, out[:, :d_out]
 
+    def build_columns_sorted(self, k, d_bases, d_offsets, n, group=None):
+        """Integer k >= 8 (kmer.py:83-85, :146-179): every k-window becomes a 128-bit key on the GPU, sorted and
+        reduced to the observed k-mers (= kmer.py's sorted() columns) and the (row, column, count) entries, which are
+        scattered into a zeroed count matrix.  Returns (columns, counts (n, D'))."""
+        self._bind_stream()
+        nk, ne = c_int64(), c_int64()
+        check(self.lib.kb_kmer_sorted_collect(self.ctx, int(k), ptr(d_bases), ptr(d_offsets), n, byref(nk), byref(ne)))
+        hi = np.zeros(nk.value, dtype=np.uint64)
+        lo = np.zeros(nk.value, dtype=np.uint64)
+        if nk.value:
+            check(self.lib.kb_kmer_sorted_fetch(self.ctx, hi.ctypes.data_as(c_void_p), lo.ctypes.data_as(c_void_p)))
+
+        def as_bytes(h, l):          # (m, 16) big-endian bytes: lexicographic order == key order == Python string order
+            return np.concatenate([h.astype(">u8").view(np.uint8).reshape(-1, 8), l.astype(">u8").view(np.uint8).reshape(-1, 8)], axis=1)
+        mine = np.ascontiguousarray(as_bytes(hi, lo)).view("S16").reshape(-1)
+        if group is not None:
+            import torch.distributed as dist
+            gathered = [None] * dist.get_world_size(group)
+            dist.all_gather_object(gathered, mine, group=group)
+            all_keys = np.unique(np.concatenate(gathered))
+        else:
+            all_keys = mine
+        raw = np.frombuffer(np.ascontiguousarray(all_keys).tobytes().ljust(16 * len(all_keys), b"\0"), dtype=np.uint8).reshape(-1, 16)[:, :k]
+        columns = [bytes(r).decode("latin-1") for r in raw]
+        d_cols = len(columns)
+        ld = max(4, (d_cols + 3) // 4 * 4)
+        counts = torch.zeros((n, ld), dtype=torch.int32, device=self.device)
+        if nk.value:
+            key_col = np.searchsorted(all_keys, mine).astype(np.int32) if group is not None else np.arange(nk.value, dtype=np.int32)
+            d_keycol = torch.from_numpy(key_col).to(self.device)
+            check(self.lib.kb_exotic_scatter(self.ctx, ptr(d_keycol), ptr(counts), ld))
+        return columns, counts[:, :d_cols]
+
     # ---- K3 ------------------------------------------------------------------------
     def normalise(self, counts, d_cols, d_key_len, want_profile=True, want_operand=True, profile=None,
                   rows_alloc=None, launch=True, presence=None, flags_or=None):
@@ -487,7 +527,10 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
     mode = mode_of(kmer_size)
     b = bufs or {}
     faithful = mode == KB_MODE_5P6 or mode >= 16
-    names = mode_column_names(mode)
+    sorted_k = is_sorted_mode(mode)
+    if sorted_k:
+        optimistic = False                              # the columns are the observed k-mers: nothing to assume
+    names = [] if sorted_k else mode_column_names(mode)
     main = torch.cuda.current_stream(engine.device)
     multi = group is not None and world > 1
     cols_full = len(names)
@@ -499,7 +542,8 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
         chunks = None
     counts = None                                       # the optimistic pass never materialises the u32 count rows
     if not optimistic:
-        counts = b.get("counts") if b.get("counts") is not None else torch.empty((n, cols_full), dtype=torch.int32, device=engine.device)
+        counts = None if sorted_k else (b.get("counts") if b.get("counts") is not None else
+                                        torch.empty((n, cols_full), dtype=torch.int32, device=engine.device))
     exotic = b.get("exotic") if b.get("exotic") is not None else torch.empty(n, dtype=torch.int32, device=engine.device)
     presence = b.get("presence") if b.get("presence") is not None else torch.empty(cols_full + 1, dtype=torch.int32, device=engine.device)
     presence.zero_()
@@ -520,6 +564,8 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
             if hi > lo and on_profile is not None and profile is not None:
                 on_profile(profile, lo, hi)
         columns = names
+    elif sorted_k:
+        columns, counts = engine.build_columns_sorted(mode - 16, d_bases, d_offsets, n, group=group if multi else None)
     else:
         engine.count(d_bases, d_offsets, n, mode, counts, exotic, presence, zero_presence=False)
         if multi:
@@ -769,6 +815,9 @@ class PassPlan:
         self.multi = group is not None and world > 1
         self.n_total = int(n_total) if self.multi else self.n
         self.mode = mode_of(kmer_size)
+        if is_sorted_mode(self.mode):
+            raise _lib.KarmaB200Error(-4, "PassPlan serves the fixed-column modes (k <= 7, 5p6, 5+6, 4+5); integer k >= 8 has "
+                                      "data-dependent columns: use device_pass / profile_and_knn")
         self.kmer_size = kmer_size
         self.faithful = self.mode == KB_MODE_5P6 or self.mode >= 16
         self.cols = check(self.lib.kb_mode_columns(self.mode))

@@ -182,3 +182,43 @@ def test_fused_count_profile_equals_count_then_normalise(engine, mode):
     assert complete == bool((pa[:-1] != 0).all())
     if not (pb[-1] & 2):
         assert np.array_equal(pa[:-1] != 0, pb[:-1] != 0)
+
+
+@pytest.mark.parametrize("k", [8, 9, 12, 16])
+def test_integer_k_beyond_7_sorted_counting(engine, k):
+    """kmer.py:83-85 takes any integer -k.  Beyond 7 the windows are counted through sorted 128-bit keys: columns =
+    the observed k-mers in sorted() order, any byte a k-mer character -- bit-exact against the pure-Python port."""
+    from karma_b200.engine import profile_and_knn
+    rng = np.random.default_rng(40 + k)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    fam = rnd(400)
+    seqs = {">c%d" % i: rnd(int(x)) for i, x in enumerate(rng.integers(k, 700, 30))}
+    seqs[">rep a"] = "ACGT" * 40
+    seqs[">withN"] = rnd(60) + "N" + rnd(50) + "nn" + rnd(30)
+    seqs[">f1"] = fam
+    seqs[">f2 x"] = fam[:200] + "T" + fam[201:]
+    seqs[">exact_k"] = rnd(k)
+    bases, offsets, key_len = ko.pack(seqs)
+    res = profile_and_knn(engine, bases, offsets, key_len, k, n_neighbors=3)
+    cols, want = ko.profile_port(seqs, k)
+    assert res["columns"] == cols
+    assert res["profile"].shape == want.shape and res["profile"].tobytes() == want.tobytes()
+    from oracle import knn_oracle
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(want))
+    assert knn_oracle.parity_ok(rep), rep
+    names = list(seqs)
+    assert res["knn_idx"][names.index(">f1"), 1] == names.index(">f2 x")
+
+
+def test_integer_k_8_full_column_space(engine):
+    """k = 8 on a few hundred random contigs: tens of thousands of observed columns, checked against the vectorised oracle."""
+    from karma_b200.engine import profile_and_knn
+    asm = synth.s0_iid(300, seed=8)
+    res = profile_and_knn(engine, asm.bases, asm.offsets, asm.key_len, 8, n_neighbors=None)
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, 8)
+    keep = counts.any(0)
+    want = counts[:, keep] / asm.key_len[:, None].astype(np.float64)
+    assert res["profile"].shape == want.shape and res["profile"].tobytes() == want.tobytes()
+    assert res["columns"] == [ko.code_to_kmer(int(c), 8) for c in np.flatnonzero(keep)]

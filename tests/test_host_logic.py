@@ -22,8 +22,11 @@ def test_mode_of_matches_reference_errors():
     assert mode_of("5p6") == _lib.KB_MODE_5P6 and mode_of(4) == _lib.KB_MODE_K(4) and mode_of(7) == 23
     with pytest.raises(TypeError):            # kmer.py:84 `len(sequence) - "4p5"`
         mode_of("4p5")
+    assert mode_of(9) == _lib.KB_MODE_K(9) and mode_of(16) == _lib.KB_MODE_K(16)      # sorted k-mer keys (k = 8..16)
     with pytest.raises(_lib.KarmaB200Error):
-        mode_of(9)
+        mode_of(17)                                # a k-mer no longer fits the 128-bit sort key
+    with pytest.raises(_lib.KarmaB200Error):
+        mode_of(0)
 
 
 def test_column_names_match_oracle_order():
