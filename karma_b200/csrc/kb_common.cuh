@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <nvtx3/nvToolsExt.h>          // header-only (NVTX v3): ranges are no-ops unless a profiler is attached
 #include "../../include/karma_b200.h"
 
 #define KB_N_TIMERS 9
@@ -56,13 +57,20 @@ int kb_cuda_fail(cudaError_t e, const char* what);
         if (!(cond)) { kb_set_error("invalid argument: %s", msg); return KB_EINVAL; } \
     } while (0)
 
+// One stage of the path on the host timeline: an NVTX range (per-stage ranges for nsys / ncu --nvtx) and,
+// with timing enabled, a CUDA-event pair on the launching stream.
+static const char* const kb_stage_names[KB_N_TIMERS] = {
+    "kb:K1 count", "kb:K1 count (split contigs)", "kb:K2 compact", "kb:K3 normalise", "kb:K4 distance GEMM + top-k",
+    "kb:K5 merge + exact rerank", "kb:K4x/K6 exact distances", "kb:read graph", "kb:group links"};
 struct KbTimer {
     kb_ctx* c; int which; int slot;
     KbTimer(kb_ctx* ctx, int w) : c(ctx), which(w), slot(0) {
+        nvtxRangePushA(kb_stage_names[which]);
         if (c->timing) { slot = c->ev_n[which] % KB_EV_RING; cudaEventRecord(c->ev0[which][slot], c->stream); }
     }
     ~KbTimer() {
         if (c->timing) { cudaEventRecord(c->ev1[which][slot], c->stream); c->ev_n[which]++; }
+        nvtxRangePop();
     }
 };
 

@@ -591,6 +591,10 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
     out = {"columns": columns, "d_cols": d_cols, "counts": counts, "profile": profile, "operand": operand,
            "rowmeta": rowmeta, "idx": None, "dist": None}
     all_op, all_meta = operand, rowmeta
+    if multi and not want_knn:
+        # every rank must reach the same verdict on the row flags (a contig shorter than k anywhere stops them all)
+        import torch.distributed as dist
+        dist.all_reduce(d_or, op=dist.ReduceOp.BOR, group=group)
     if want_knn and multi:
         # the one exchange step: every rank needs all keys -- the fp16 operand shards and the 32-byte row records
         all_op = all_gather_rows(operand, group)
@@ -639,12 +643,21 @@ def _device_pass(engine, d_bases, d_offsets, d_key_len, n, kmer_size="5p6", n_ne
                     flag_counts = local
                 flag_rows = torch.from_numpy(ids).to(engine.device)
         q_row0 = rank * per if multi else 0
-        idx, dst, _, fixup = engine.knn_enqueue(all_op, all_meta, n_neighbors, q_row0=q_row0, nq=n, impl=impl,
-                                                flag_rows=flag_rows, flag_counts=flag_counts)
-        impl_used = impl if impl != KB_KNN_AUTO else (_lib.KB_KNN_TC if all_op.shape[0] >= 512 else _lib.KB_KNN_SIMT)
-        unc_addr = engine.uncertified_word(n, all_op.shape[0], q_row0, all_op.shape[1], n_neighbors, impl_used,
-                                           0 if flag_rows is None else int(flag_rows.numel()))
-        d_unc = engine.word_view(unc_addr)
+        if n > 0:
+            idx, dst, _, fixup = engine.knn_enqueue(all_op, all_meta, n_neighbors, q_row0=q_row0, nq=n, impl=impl,
+                                                    flag_rows=flag_rows, flag_counts=flag_counts)
+            impl_used = impl if impl != KB_KNN_AUTO else (_lib.KB_KNN_TC if all_op.shape[0] >= 512 else _lib.KB_KNN_SIMT)
+            unc_addr = engine.uncertified_word(n, all_op.shape[0], q_row0, all_op.shape[1], n_neighbors, impl_used,
+                                               0 if flag_rows is None else int(flag_rows.numel()))
+            d_unc = engine.word_view(unc_addr)
+        else:
+            # a rank without rows (fewer contigs than ranks) still takes part in every collective
+            idx = torch.empty((0, n_neighbors), dtype=torch.int32, device=engine.device)
+            dst = torch.empty((0, n_neighbors), dtype=torch.float32, device=engine.device)
+            d_unc = torch.zeros(1, dtype=torch.int32, device=engine.device)
+
+            def fixup():
+                return 0
 
         def gather_all_lists():
             # k-lists back to every rank: [idx | dist bits] packed per row, plus one row-block that carries

@@ -108,9 +108,11 @@ def umap_embedding(profile, knn_indices, knn_dists, umap_args, umap_module=None)
 
 
 class KmerClustering:
-    """Mirror of kmer.py's class.  ``kmer_size``: "5p6" (kmer.py's default), any integer k >= 1 (kmer.py:83-85;
-    k <= 7 count into dense shared-memory histograms, larger k through sorted k-mer codes), or the fixed-column
-    throughput shapes "5+6" / "4+5" of this library (A/C/G/T only: other bytes are rejected there)."""
+    """Mirror of kmer.py's class.  ``kmer_size``: "5p6" (kmer.py's default), an integer k (kmer.py:83-85): k <= 7
+    counts into dense shared-memory histograms, 8 <= k <= 16 through sorted 128-bit k-mer keys, k > 16 raises
+    KarmaB200Error (the sort key holds 16 characters); or the fixed-column throughput shapes "5+6" / "4+5" of this
+    library (A/C/G/T only: other bytes are rejected there).  Sequences must be single-byte characters (latin-1;
+    FASTA is ASCII): one byte per character keeps byte order == the code-point order sorted() uses (kmer.py:172)."""
 
     def __init__(self, sequences, output_dir, kmer_size, threads):
         # kmer.py:15-27
