@@ -336,11 +336,16 @@ def big_run(torch, dist, eng, a, n_total, rank, world, local, pk):
     h_len = torch.from_numpy(shard.key_len.copy()).pin_memory()
     plan = PassPlan(eng, shard.n, int(shard.offsets[-1]), kmer, n_neighbors=k, impl=_lib.KB_KNN_TC, want_profile=True,
                     group=dist.group.WORLD if world > 1 else None, rank=rank, world=world, n_total=n_total, graph=False)
+    def note(msg):
+        if rank == 0:
+            print("[bench big %d] %s" % (n_total, msg), file=sys.stderr, flush=True)
     try:
+        note("plan ready (synth %.1f s)" % gen_s)
         plan.load(h_bases, h_off, h_len)
         eng.enable_timing(True)
         tok = plan.run()                                        # warm-up (uploads the piece table)
         first = plan.check(tok)
+        note("first pass done: %r" % (first,))
         for st in ("count", "normalise", "knn_gemm", "rerank"):
             eng.stage_ms(st)
         ms, checks = timed_plan_loop(torch, dist, plan, 2, world)
@@ -349,6 +354,7 @@ def big_run(torch, dist, eng, a, n_total, rank, world, local, pk):
         norm_ms, _ = eng.stage_ms("normalise")
         rerank_ms, _ = eng.stage_ms("rerank")
         eng.enable_timing(False)
+        note("timed passes done: %.1f ms per pass" % (ms / 2))
         if any(not c["ok"] for c in checks + [first]):
             raise RuntimeError("optimistic validation failed on the synthetic shard: %r" % (checks,))
         # rows K5 could not certify are redone exactly (all ranks take part: the count is the sum over ranks)
@@ -382,6 +388,7 @@ def big_run(torch, dist, eng, a, n_total, rank, world, local, pk):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s, fix_s = float(tt[0].item()), float(tt[1].item())
+        note("host-to-host pass done: %.1f ms (exact redo %.1f ms)" % (e2e_s * 1e3, fix_s * 1e3))
         if not last["ok"]:
             raise RuntimeError("optimistic validation failed on the synthetic shard: %r" % (last,))
         rec = None

@@ -295,13 +295,16 @@ KB_API int kb_knn_plan_table(int sm_count, int impl, int64_t nq, int64_t nk, int
  *   kb_xchg_finish   on the context stream after K5: copy this rank's record (rec_words u32 at
  *                    rec_off + rank*rec_words*4) to every peer, raise the results flag everywhere and wait
  *                    until every peer's results and record have landed here
- * All waits are bounded (a dead peer traps the kernel after ~10 s instead of hanging the GPU). */
+ * All waits are bounded (a dead peer traps the kernel after ~30 s instead of hanging the GPU). */
 typedef struct kb_xchg kb_xchg;
 KB_API int kb_xchg_create(kb_ctx* ctx, int world, int rank, int64_t bytes, kb_xchg** out, void** d_local, uint8_t* handle64);
 KB_API int kb_xchg_attach(kb_xchg* x, const uint8_t* handles);
 KB_API int kb_xchg_peer_ptr(kb_xchg* x, int peer, void** d_ptr);
 KB_API int kb_xchg_flags(kb_xchg* x, const uint32_t** d_arrive, const uint32_t** d_epoch);
 KB_API int kb_xchg_destroy(kb_xchg* x);
+/* once after kb_xchg_attach: memset this rank's shard of every region in every peer's arena and synchronise, so that
+ * the peer mappings of a fresh multi-gigabyte arena are set up before the first pass */
+KB_API int kb_xchg_warm(kb_xchg* x, int n_regions, const int64_t* region_off, const int64_t* shard_bytes);
 KB_API int kb_xchg_begin(kb_xchg* x);
 KB_API int kb_xchg_push(kb_xchg* x, void* stream, int n_regions, const int64_t* region_off, const int64_t* shard_bytes);
 KB_API int kb_xchg_finish(kb_xchg* x, int64_t rec_off, int32_t rec_words);

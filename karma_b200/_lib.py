@@ -63,6 +63,7 @@ SIGNATURES = {
     "kb_xchg_peer_ptr": (c_int, [_P, c_int, POINTER(c_void_p)]),
     "kb_xchg_flags": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p)]),
     "kb_xchg_destroy": (c_int, [_P]),
+    "kb_xchg_warm": (c_int, [_P, c_int, _P, _P]),
     "kb_xchg_begin": (c_int, [_P]),
     "kb_xchg_push": (c_int, [_P, _P, c_int, _P, _P]),
     "kb_xchg_finish": (c_int, [_P, c_int64, c_int32]),

@@ -62,7 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     const long long t0 = clock64();
     uint32_t it = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++it & 0x3ff) == 0 && clock64() - t0 > 6000000000LL) {
+        if ((++it & 0x3ff) == 0 && clock64() - t0 > 90000000000LL) {      // ~45 s: longer than the wait for a peer's shard
             printf("kb_knn_tc: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
             __trap();
         }
@@ -176,8 +176,8 @@ __device__ __forceinline__ void wait_row_arrived(const TcParams& p, uint32_t epo
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
         if ((int32_t)(v - epoch) >= 0) break;
-        if ((++it & 0xff) == 0 && clock64() - t0 > 12000000000LL) {
-            printf("kb_knn_tc: shard of rank %d never arrived (tag %d, block %d)\n", src, tag, blockIdx.x);
+        if ((++it & 0xff) == 0 && clock64() - t0 > 60000000000LL) {        // ~30 s
+            printf("kb_knn_tc: shard of rank %d never arrived (tag %d, block %d): flag %u, epoch %u\n", src, tag, blockIdx.x, v, epoch);
             __trap();
         }
         __nanosleep(64);
@@ -455,7 +455,9 @@ struct Smem2 {
     static constexpr int OFF_BARS = OFF_COLMETA + BN * 8;
     static constexpr int OFF_TMEM_SLOT = OFF_BARS + (2 * STAGES + 4) * 8;
     static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
-    static_assert(TOTAL <= 232448, "more shared memory than an SM has");
+    // 224 KB at most: with a peer exchange the tiny flag kernels of kb_xchg.cu (1 KB of system shared memory each) must
+    // find room on an SM NEXT TO a resident CTA of this persistent kernel -- it waits for the very flags they raise
+    static_assert(TOTAL <= 229376, "leave 4 KB of the SM's 228 KB to the exchange's flag kernels");
 };
 
 template <int KP, int STAGES, int QCAP>
@@ -731,16 +733,17 @@ int launch_tc2(kb_ctx* ctx, const CUtensorMap& tmap, const TcParams& prm, int wo
 // row; the wide lists (48, 64: n_neighbors 27..60) take the room of two stages (one for the 48 KB stages)
 template <int KP>
 int launch_tc_kp(kb_ctx* ctx, const CUtensorMap& tmap, const CUtensorMap& tmap_b, int cl, const TcParams& prm, int workers) {
-    // 32 KB stages next to the lists and the insertion queues (16 entries per row = 16 KB): 6 stages up to 16-wide
-    // lists, 5 for 24 / 32, 4 for 48 / 64.  Wide rows (>= 2560 columns: long MMA tiles, light epilogue) with 24-wide
-    // lists trade half the queue for the sixth stage (5120 columns, k = 15: 1385 -> 14xx TFLOP/s).
+    // 32 KB stages next to the lists and the insertion queues (16 entries per row = 16 KB; 12 for 16-wide lists):
+    // 6 stages up to 16-wide lists, 5 for 24 / 32, 4 for 48 / 64.  Wide rows (>= 2560 columns: long MMA tiles, light
+    // epilogue) with 24-wide lists trade most of the queue for the sixth stage.
     constexpr int ST2 = KP <= 16 ? 6 : (KP <= 32 ? 5 : 4);
+    constexpr int Q2 = KP == 16 ? 12 : 16;
     constexpr int ST1 = KP <= 32 ? 4 : 3;
     // CTA pairs run one 2-CTA MMA (k4_tc2) unless KB_KNN_MMA2=0 asks for the two-MMA multicast kernel (experiments)
     const char* m2 = getenv("KB_KNN_MMA2");
     if (cl == 2 && !(m2 && atoi(m2) == 0)) {
-        if constexpr (KP == 24) { if (prm.k_blocks >= 40) return launch_tc2<24, 6, 8>(ctx, tmap, prm, workers); }
-        return launch_tc2<KP, ST2, 16>(ctx, tmap, prm, workers);
+        if constexpr (KP == 24) { if (prm.k_blocks >= 40) return launch_tc2<24, 6, 4>(ctx, tmap, prm, workers); }
+        return launch_tc2<KP, ST2, Q2>(ctx, tmap, prm, workers);
     }
     if (cl == 4) return launch_tc<KP, ST1, 4>(ctx, tmap, tmap_b, prm, workers);
     if (cl == 2) return launch_tc<KP, ST1, 2>(ctx, tmap, tmap_b, prm, workers);

@@ -57,8 +57,8 @@ __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t want, int wh
     const long long t0 = clock64();
     uint32_t it = 0;
     while ((int32_t)(ld_acquire_sys(p) - want) < 0) {
-        if ((++it & 0xff) == 0 && clock64() - t0 > 20000000000LL) {
-            printf("kb_xchg: timed out waiting for flag %d of rank %d (want %u)\n", what, who, want);
+        if ((++it & 0xff) == 0 && clock64() - t0 > 40000000000LL) {
+            printf("kb_xchg: timed out waiting for flag %d of rank %d (want %u, have %u)\n", what, who, want, ld_acquire_sys(p));
             __trap();
         }
         __nanosleep(100);
@@ -176,6 +176,24 @@ extern "C" int kb_xchg_destroy(kb_xchg* x) {
     cudaFree(x->d_peer);
     cudaFree(x->local);
     free(x);
+    return KB_OK;
+}
+
+// Touch every peer's copy of this rank's shard regions once (a memset over NVLink) and synchronise: the first access to a
+// freshly IPC-mapped multi-gigabyte arena sets up its peer mappings, which must not happen inside the first pass where
+// kernels wait (bounded) for the data.
+extern "C" int kb_xchg_warm(kb_xchg* x, int n_regions, const int64_t* region_off, const int64_t* shard_bytes) {
+    KB_CHECK_ARG(x && x->attached && n_regions >= 0 && (n_regions == 0 || (region_off && shard_bytes)), "arguments");
+    KB_CUDA(cudaSetDevice(x->ctx->device));
+    for (int p = 0; p < x->world; ++p) {
+        if (p == x->rank) continue;
+        for (int r = 0; r < n_regions; ++r) {
+            const int64_t off = region_off[r] + (int64_t)x->rank * shard_bytes[r];
+            KB_CHECK_ARG(off >= (int64_t)sizeof(KbXchgCtrl) && off + shard_bytes[r] <= x->bytes, "region outside the arena");
+            if (shard_bytes[r]) KB_CUDA(cudaMemsetAsync(x->peer[p] + off, 0, (size_t)shard_bytes[r], x->ctx->stream));
+        }
+    }
+    KB_CUDA(cudaStreamSynchronize(x->ctx->stream));
     return KB_OK;
 }
 
