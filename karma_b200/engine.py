@@ -888,6 +888,8 @@ class PassPlan:
         self._step = 0
         self.graph = None
         self._want_graph = bool(graph)
+        self._io = None                                         # host-to-host pass (bind_host / run_host)
+        self.host = None
 
     # ---- exchange set-up (once) -----------------------------------------------------------
     def _setup_exchange(self, k):
@@ -957,6 +959,8 @@ class PassPlan:
         if self.x is not None:
             torch.cuda.synchronize(self.engine.device)
             self.graph = None
+            if self._io is not None:
+                self._io["graph"] = None
             self.lib.kb_xchg_destroy(self.x)
             self.x = None
 
@@ -975,21 +979,55 @@ class PassPlan:
             self.d_key_len.copy_(t(key_len, np.int32), non_blocking=True)
 
     # ---- one pass ---------------------------------------------------------------------------
-    def enqueue(self):
-        """K1 -> K3 -> [push] -> K4 -> K5 -> [finish] on the current stream.  No allocation, no synchronisation."""
+    def enqueue(self, host_io=False):
+        """K1 -> K3 -> [push] -> K4 -> K5 -> [finish] on the current stream.  No allocation, no synchronisation.
+        ``host_io`` (after `bind_host`): the pass starts from the pinned host inputs and ends with the float64
+        profile rows, this rank's k-lists and the validation words in pinned host memory -- the bases go up in row
+        chunks on a copy stream, every chunk is counted as it lands and its profile rows start their download on a
+        second copy stream (the other DMA direction) while the remaining uploads, the exchange and the kNN run."""
         e, lib = self.engine, self.lib
         e._bind_stream()
         main = torch.cuda.current_stream(e.device)
+        io = self._io if host_io else None
+        if io is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            io["up"].wait_event(fork)
+            io["down"].wait_event(fork)
+            landed = []
+            with torch.cuda.stream(io["up"]):
+                self.d_offsets.copy_(io["h_offsets"], non_blocking=True)
+                if self.n:
+                    self.d_key_len.copy_(io["h_key_len"], non_blocking=True)
+                for (lo, hi, b0, b1) in io["chunks"]:
+                    if b1 > b0:
+                        self.d_bases[b0:b1].copy_(io["h_bases"][b0:b1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(io["up"])
+                    landed.append(ev)
         if self.x is not None:
             check(lib.kb_xchg_begin(self.x))
         self.rec.zero_()                                        # flags, uncertified rows and the presence vector
         n_alloc = self.per if self.x is not None else self.n
-        lo = self.q_row0
+        q0 = self.q_row0
         # K1+K3 fused: the histogram of every contig goes straight to its profile / operand / record rows
-        check(lib.kb_count_profile(e.ctx, self.mode, ptr(self.d_bases), ptr(self.d_offsets), ptr(self.d_key_len), self.n, n_alloc,
-                                   ptr(self.profile) if self.profile is not None and self.n else None, self.cols,
-                                   ptr(self.operand_all[lo:]) if self.want_knn else None, self.dp,
-                                   ptr(self.rowmeta_all[lo:]), ptr(self.exotic), ptr(self.presence), ptr(self.rec)))
+        for c, (lo, hi, _, _) in enumerate(io["chunks"] if io is not None else [(0, self.n, 0, 0)]):
+            if io is not None:
+                main.wait_event(landed[c])
+            rows_out = (n_alloc if hi == self.n else hi) - lo   # the last chunk also writes the gather padding rows
+            if rows_out > 0:
+                check(lib.kb_count_profile(e.ctx, self.mode, ptr(self.d_bases), ptr(self.d_offsets[lo:]),
+                                           ptr(self.d_key_len[lo:]) if hi > lo else None, hi - lo, rows_out,
+                                           ptr(self.profile[lo:]) if self.profile is not None and hi > lo else None, self.cols,
+                                           ptr(self.operand_all[q0 + lo:]) if self.want_knn else None, self.dp,
+                                           ptr(self.rowmeta_all[q0 + lo:]), ptr(self.exotic[lo:]) if hi > lo else None,
+                                           ptr(self.presence), ptr(self.rec)))
+            if io is not None and self.profile is not None and hi > lo:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                io["down"].wait_event(ev)
+                with torch.cuda.stream(io["down"]):
+                    io["h_profile"][lo:hi].copy_(self.profile[lo:hi], non_blocking=True)
         if self.x is not None:
             ev = torch.cuda.Event()
             ev.record(main)
@@ -1003,6 +1041,96 @@ class PassPlan:
         if self.x is not None:
             check(lib.kb_xchg_finish(self.x, self._lay["rec"], self.rec_words))
             main.wait_stream(self.side)
+        if io is not None:
+            # small results last: they queue behind the profile rows on the D2H copy engine and must not hold back K4
+            if self.want_knn and self.n:
+                io["h_idx"].copy_(self.idx, non_blocking=True)
+                io["h_dist"].copy_(self.dist, non_blocking=True)
+            io["h_rec"].copy_(self.rec_all, non_blocking=True)
+            main.wait_stream(io["up"])
+            main.wait_stream(io["down"])
+
+    # ---- host-to-host passes ----------------------------------------------------------------
+    def bind_host(self, bases, offsets, key_len, chunks=4):
+        """Stage this rank's contigs (host arrays / tensors) in the plan's pinned input buffers and plan the
+        host-to-host pass for them: row chunks of about equal bases.  The pinned buffers (``plan.host["h_bases"]``,
+        ``["h_offsets"]``, ``["h_key_len"]``) may afterwards be rewritten in place with other contigs of the SAME
+        offsets; a different set of contig lengths needs another `bind_host` (the chunk bounds are part of the
+        captured graph).  Results of `run_host` land in ``plan.host["h_profile" | "h_idx" | "h_dist"]``."""
+        dev = self.engine.device
+
+        def t(a, dtype):
+            return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+        o = t(offsets, np.int64)
+        total = int(o[-1])
+        if o.numel() != self.n + 1 or _round_up(total, 16) + 32 > self.d_bases.numel():
+            raise ValueError("PassPlan was planned for %d contigs / %d bases" % (self.n, self.d_bases.numel() - 32))
+        io = self._io
+        if io is None:
+            k = self.k or 1
+            io = {"up": torch.cuda.Stream(dev), "down": torch.cuda.Stream(dev),
+                  "h_bases": torch.zeros(self.d_bases.numel(), dtype=torch.uint8, pin_memory=True),
+                  "h_offsets": torch.zeros(self.n + 1, dtype=torch.int64, pin_memory=True),
+                  "h_key_len": torch.ones(max(self.n, 1), dtype=torch.int32, pin_memory=True),
+                  "h_profile": torch.empty((self.n, self.cols), dtype=torch.float64, pin_memory=True) if self.profile is not None else None,
+                  "h_idx": torch.empty((self.n, k), dtype=torch.int32, pin_memory=True) if self.want_knn else None,
+                  "h_dist": torch.empty((self.n, k), dtype=torch.float32, pin_memory=True) if self.want_knn else None,
+                  "h_rec": torch.zeros(tuple(self.rec_all.shape), dtype=torch.int32, pin_memory=True),
+                  "done": torch.cuda.Event(), "chunks": None, "graph": None}
+            self._io = io
+            self.host = io
+        hb = t(bases, np.uint8)
+        if hb.data_ptr() != io["h_bases"].data_ptr():
+            io["h_bases"][:total].copy_(hb[:total])
+        if o.data_ptr() != io["h_offsets"].data_ptr():
+            io["h_offsets"].copy_(o)
+        if self.n and t(key_len, np.int32).data_ptr() != io["h_key_len"].data_ptr():
+            io["h_key_len"].copy_(t(key_len, np.int32))
+        # row chunks of about equal bases; byte bounds widened to 16 so that every copy is aligned
+        on = io["h_offsets"].numpy()
+        c = max(1, min(int(chunks), self.n // 1024 if self.n >= 2048 else 1))
+        cuts = [0] + [int(np.searchsorted(on, total * i / c)) for i in range(1, c)] + [self.n]
+        cuts = sorted(set(min(max(x, 0), self.n) for x in cuts))
+        if len(cuts) == 1:
+            cuts = [0, self.n]
+        plan = [(lo, hi, int(on[lo]), int(on[hi])) for lo, hi in zip(cuts[:-1], cuts[1:])]
+        if plan != io["chunks"]:
+            io["chunks"] = plan
+            io["graph"] = None
+
+    def run_host(self):
+        """One host-to-host pass over the bound inputs (one graph replay when the plan is graph-captured), waited
+        for and validated.  Returns dict(ok, flags_or, uncertified, exotic, complete, profile, knn_idx, knn_dist):
+        numpy views of the plan's pinned result buffers, overwritten by the next call.  Every rank calls it at
+        the same point."""
+        io = self._io
+        e = self.engine
+        if self._want_graph and io["graph"] is None:
+            timing = e.timing_enabled
+            e.enable_timing(False)
+            self.enqueue(host_io=True)
+            torch.cuda.synchronize(e.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue(host_io=True)
+            io["graph"] = g
+            e._bind_stream()
+            torch.cuda.synchronize(e.device)
+            e.enable_timing(timing)
+            if self.multi:
+                import torch.distributed as dist
+                dist.barrier(group=self.group)
+        if io["graph"] is not None:
+            io["graph"].replay()
+        else:
+            self.enqueue(host_io=True)
+        io["done"].record(torch.cuda.current_stream(e.device))
+        io["done"].synchronize()
+        out = self._verdict(io["h_rec"].numpy())
+        out["profile"] = io["h_profile"].numpy() if io["h_profile"] is not None else None
+        out["knn_idx"] = io["h_idx"].numpy() if io["h_idx"] is not None else None
+        out["knn_dist"] = io["h_dist"].numpy() if io["h_dist"] is not None else None
+        return out
 
     def capture(self, warmup=2):
         """Warm up eagerly (uploads the K4 piece table, sizes scratch buffers), then capture the pass in a CUDA
@@ -1044,7 +1172,9 @@ class PassPlan:
             raise ValueError("the validation words of that pass have been overwritten")
         slot = token & 1
         self._events[slot].synchronize()
-        v = self.h_val[slot].numpy()
+        return self._verdict(self.h_val[slot].numpy())
+
+    def _verdict(self, v):
         flags_or = int(np.bitwise_or.reduce(v[:, 0]))
         unc = int(v[:, 1].sum())
         pres = np.bitwise_or.reduce(v[:, 4:], axis=0)            # OR over the ranks: column words, [D] = exotic | complete bits

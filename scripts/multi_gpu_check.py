@@ -69,6 +69,14 @@ def main():
             print("rank %d plan pass %d: own rows == eager path %s, profile %s, check %r" % (rank, it, same, prof_same, chk))
         plan_all_idx = plan.all_idx.cpu().numpy()[:asm.n]
         plan_all_dist = plan.all_dist.cpu().numpy()[:asm.n]
+        # the host-to-host form of the same pass (pinned inputs in, pinned results out, one graph): twice
+        plan.bind_host(shard.bases, shard.offsets, shard.key_len, chunks=3)
+        for it in range(2):
+            hr = plan.run_host()
+            same = hr["ok"] and np.array_equal(hr["knn_idx"], res["knn_idx"]) and np.array_equal(hr["knn_dist"], res["knn_dist"]) \
+                and hr["profile"].tobytes() == res["profile"].tobytes()
+            plan_ok &= bool(same)
+            print("rank %d host pass %d: == eager path %s" % (rank, it, same))
         plan.close()
     else:
         plan_all_idx = plan_all_dist = None
