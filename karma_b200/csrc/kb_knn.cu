@@ -181,7 +181,7 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, 
     p->off_rowthr = off;  off += kb_round_up(nq * (int64_t)sizeof(int32_t), 256);
     p->off_xidx = off;    off += (n_flag > 0 && p->kp) ? kb_round_up(nq * p->kp * (int64_t)sizeof(int32_t), 256) : 0;
     p->off_xd2 = off;     off += (n_flag > 0 && p->kp) ? kb_round_up(nq * p->kp * (int64_t)sizeof(double), 256) : 0;
-    p->off_uncert = off;  off += kb_round_up((nq + 4) * (int64_t)sizeof(int32_t), 256);    // [0] count, [4..] rows
+    p->off_uncert = off;  off += kb_round_up((nq + 4) * (int64_t)sizeof(int32_t), 256);    // [0] count, [1] Gram entries recomputed by K5, [4..] rows
     p->total = off;
     return KB_OK;
 }
@@ -271,7 +271,7 @@ k4_init(int32_t* __restrict__ row_thr, int64_t nq, int32_t* __restrict__ uncert,
         row_thr[j] = 0x7f800000;                              // +inf as an ordered-int key
         if (mark_all) uncert[4 + j] = (int32_t)j;
     }
-    if (j == 0) uncert[0] = mark_all ? (int32_t)nq : 0;
+    if (j == 0) { uncert[0] = mark_all ? (int32_t)nq : 0; uncert[1] = 0; }   // [1]: Gram entries K5 took from the operand rows
 }
 
 // ---------------------------------------------------------------------------
@@ -368,7 +368,12 @@ k4_simt(const __half* __restrict__ op, int64_t ld, int32_t dp,
 // ---------------------------------------------------------------------------
 struct K5Peers { int32_t n; int32_t* const* idx; float* const* dist; };
 
-template <int KP>
+#ifndef KB_K5_ALWAYS_DOT
+#define KB_K5_ALWAYS_DOT 0     // 1: recompute every Gram entry from the operand rows (the pre-r02 rerank; A/B and checks)
+#endif
+
+// MAXC: candidates per lane the merge holds (slots*KP <= 32*MAXC; the launcher picks the smallest that fits)
+template <int KP, int MAXC>
 __global__ void __launch_bounds__(256)
 k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
                 const kb_rowmeta* __restrict__ rowmeta, int64_t q_row0, int64_t nq, int slots, int32_t k,
@@ -377,7 +382,6 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
                 const int32_t* __restrict__ extra_idx, const double* __restrict__ extra_d2,
                 int32_t* __restrict__ out_idx, float* __restrict__ out_dist, double* __restrict__ out_d2,
                 int32_t* __restrict__ uncert, K5Peers peers) {
-    constexpr int MAXC = KB_KNN_MAX_CAND / 32;               // slots*KP <= 32*MAXC
     constexpr int NS = (KP + 31) / 32;                       // merged candidates per lane
     const int lane = threadIdx.x & 31;
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -395,30 +399,30 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
         else { cs[u] = INF; ci[u] = -1; }
         if (ci[u] < 0) cs[u] = INF;
     }
-    int32_t my_idx[NS];
+    int32_t my_idx[NS]; float my_sc[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) my_idx[s] = -1;
+    for (int s = 0; s < NS; ++s) { my_idx[s] = -1; my_sc[s] = INF; }
     float m_last = INF;                                       // score of the KP-th merged candidate (+inf: fewer exist)
     for (int r = 0; r < KP; ++r) {
         float best = INF; int32_t bidx = 0x7fffffff; int bu = -1;
 #pragma unroll
         for (int u = 0; u < MAXC; ++u)
             if (ci[u] >= 0 && (cs[u] < best || (cs[u] == best && ci[u] < bidx))) { best = cs[u]; bidx = ci[u]; bu = u; }
-        // warp arg-min over (score, idx)
-        float wb = best; int32_t wi = bidx; int wl = lane;
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, wb, o);
-            const int32_t oi = __shfl_xor_sync(0xffffffffu, wi, o);
-            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-            if (ob < wb || (ob == wb && oi < wi)) { wb = ob; wi = oi; wl = ol; }
-        }
+        // warp arg-min over (score, idx): two integer min-reductions (order-preserving key of the score, then the
+        // index among the lanes that hold that score) instead of a 5-step shuffle ladder over three values
+        const int32_t kb_ = __float_as_int(best);
+        const int32_t kbest = kb_ >= 0 ? kb_ : kb_ ^ 0x7fffffff;
+        const int32_t wk = __reduce_min_sync(0xffffffffu, kbest);
+        const int32_t wi = __reduce_min_sync(0xffffffffu, kbest == wk ? bidx : 0x7fffffff);
+        const int wl = __ffs(__ballot_sync(0xffffffffu, kbest == wk && bidx == wi)) - 1;
+        const float wb = __int_as_float(wk >= 0 ? wk : wk ^ 0x7fffffff);
         if (wi == 0x7fffffff) break;                          // nothing left anywhere
         if (lane == wl) {
 #pragma unroll
             for (int u = 0; u < MAXC; ++u) if (u == bu) ci[u] = -1;   // consume
         }
 #pragma unroll
-        for (int s = 0; s < NS; ++s) if (r == lane + 32 * s) my_idx[s] = wi;
+        for (int s = 0; s < NS; ++s) if (r == lane + 32 * s) { my_idx[s] = wi; my_sc[s] = wb; }
         if (r == KP - 1) m_last = wb;
     }
     // ---- 2. exact-side-path extras (rows the tensor path cannot score exactly): lane e also
@@ -454,23 +458,49 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 #pragma unroll
         for (int s = 0; s < NS; ++s) if (lane + 32 * s == KP - 1) my_idx[s] = self;
     }
-    // ---- 3. exact distances: all lanes cooperate on one candidate at a time.
+    // ---- 3. exact distances.
     //   sum_c (a_c*lj - b_c*lq)^2 = lj^2*n_q + lq^2*n_j - 2*lj*lq*g,  g = sum_c a_c*b_c.
-    //   Rows that reach this point are unflagged: counts <= 2048 and n < 2^24, hence
-    //   g <= sqrt(n_q*n_j) < 2^24 and every partial sum of the fp32 dot product is an
-    //   exactly representable integer -- the fp32 FMA chain IS the exact integer Gram entry.
+    //   Rows that reach this point are unflagged: counts <= 2048 and n < 2^24, hence g <= sqrt(n_q*n_j) < 2^24 is an
+    //   integer the candidate kernels hold EXACTLY (fp32 accumulation of integer products), and the score they
+    //   stored is s = RN(g*cm_x + RN(l_q*cm_y)) -- one FMUL, one FFMA (kb_score), both reproducible here.  So the
+    //   Gram entry is read back out of the score instead of being recomputed from two 2*dp-byte operand rows:
+    //   g0 = rint((s - t)/cm_x); RN(g*cm_x + t) is monotone in g, so when g0 reproduces s and g0-1, g0+1 do not,
+    //   g0 is the only integer that maps to s, i.e. the Gram entry itself.  Candidates for which that test fails
+    //   (score spacing coarser than |cm_x|: very long contigs against short keys) take the operand rows (the
+    //   fp32 FMA chain below IS the exact integer dot product for unflagged rows).
     //   The three terms are exact integers in fp64 (< 2^53), so d2 has one rounding (the division).
     const __half* qrow = op + (int64_t)self * ld;
     const double lq = (double)mq.key_len;
+    const float lqf = (float)mq.key_len;
     double my_d2[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) my_d2[s] = 0.0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        for (int e = 0; e < 32 && e + 32 * s < KP; ++e) {
-            const int32_t j = __shfl_sync(0xffffffffu, my_idx[s], e);
-            if (j < 0 || j == self) continue;                 // d2(self) = 0 exactly
-            const __half* krow = op + (int64_t)j * ld;
+        const int32_t j = my_idx[s];
+        bool need_dot = false;
+        kb_rowmeta mj; mj.sqnorm = 0.0; mj.key_len = 1; mj.cm_x = -1.f; mj.cm_y = 0.f;
+        if (lane + 32 * s < KP && j >= 0 && j != self) {      // d2(self) = 0 exactly
+            mj = rowmeta[j];
+            const float t = __fmul_rn(lqf, mj.cm_y);
+            const float sc = my_sc[s];
+            const float g = (float)rint(((double)sc - (double)t) / (double)mj.cm_x);
+            const bool unique = g >= 0.f && g < 16777216.f && __fmaf_rn(g, mj.cm_x, t) == sc &&
+                                __fmaf_rn(g + 1.f, mj.cm_x, t) != sc && __fmaf_rn(g - 1.f, mj.cm_x, t) != sc;
+            if (unique && !KB_K5_ALWAYS_DOT) {
+                const double lj = (double)mj.key_len;
+                const double num = lj * lj * mq.sqnorm + lq * lq * mj.sqnorm - 2.0 * (lj * lq) * (double)g;
+                my_d2[s] = num / ((lq * lj) * (lq * lj));
+            } else {
+                need_dot = true;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, need_dot);
+        while (todo) {                                        // all lanes cooperate on one candidate at a time
+            const int e = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int32_t jj = __shfl_sync(0xffffffffu, j, e);
+            const __half* krow = op + (int64_t)jj * ld;
             float g0 = 0.f, g1 = 0.f;
             for (int c = 8 * lane; c < dp; c += 256) {
                 const uint4 a = *reinterpret_cast<const uint4*>(qrow + c);
@@ -487,10 +517,10 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
             float g = g0 + g1;
             for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
             if (lane == e) {
-                const kb_rowmeta mj = rowmeta[j];
                 const double lj = (double)mj.key_len;
                 const double num = lj * lj * mq.sqnorm + lq * lq * mj.sqnorm - 2.0 * (lj * lq) * (double)g;
                 my_d2[s] = num / ((lq * lj) * (lq * lj));
+                atomicAdd(&uncert[1], 1);
             }
         }
     }
@@ -858,12 +888,20 @@ int run_rerank(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, in
                const kb_rowmeta* rowmeta, int64_t q_row0, int64_t nq, int32_t k, uint8_t* ws, bool extras,
                const int32_t* slot_count, int32_t* d_idx, float* d_dist, double* d_d2, K5Peers peers) {
     const int64_t grid = (nq + 7) / 8;
-    k5_merge_rerank<KP><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-        op, ld, dp, rowmeta, q_row0, nq, p.slots, k, slot_count, p.bm * p.cl,
-        reinterpret_cast<const float*>(ws + p.off_score), reinterpret_cast<const int32_t*>(ws + p.off_idx),
-        extras ? reinterpret_cast<const int32_t*>(ws + p.off_xidx) : nullptr,
-        extras ? reinterpret_cast<const double*>(ws + p.off_xd2) : nullptr, d_idx, d_dist, d_d2,
-        reinterpret_cast<int32_t*>(ws + p.off_uncert), peers);
+    const int per_lane = (p.slots * KP + 31) / 32;
+#define K5_LAUNCH(MC)                                                                                              \
+    k5_merge_rerank<KP, MC><<<(unsigned)grid, 256, 0, ctx->stream>>>(                                              \
+        op, ld, dp, rowmeta, q_row0, nq, p.slots, k, slot_count, p.bm * p.cl,                                      \
+        reinterpret_cast<const float*>(ws + p.off_score), reinterpret_cast<const int32_t*>(ws + p.off_idx),        \
+        extras ? reinterpret_cast<const int32_t*>(ws + p.off_xidx) : nullptr,                                      \
+        extras ? reinterpret_cast<const double*>(ws + p.off_xd2) : nullptr, d_idx, d_dist, d_d2,                   \
+        reinterpret_cast<int32_t*>(ws + p.off_uncert), peers)
+    if (per_lane <= 1) K5_LAUNCH(1);
+    else if (per_lane <= 2) K5_LAUNCH(2);
+    else if (per_lane <= 4) K5_LAUNCH(4);
+    else if (per_lane <= 8) K5_LAUNCH(8);
+    else K5_LAUNCH(KB_KNN_MAX_CAND / 32);
+#undef K5_LAUNCH
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;

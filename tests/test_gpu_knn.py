@@ -281,3 +281,42 @@ def test_redundant_merge_200k_5120_k15(engine):
     truth = num / np.outer(l[rows], l) ** 2
     rep = knn_oracle.check_knn(idx[rows], dist[rows], truth, rows=rows)
     assert knn_oracle.parity_ok(rep), rep
+
+
+def test_rerank_reads_the_gram_entry_out_of_the_score_or_recomputes_it(engine):
+    """K5 recovers the exact integer Gram entry from a candidate's fp32 score when exactly one integer maps to that
+    score, and recomputes it from the operand rows otherwise.  Ordinary assemblies never need the second path; huge
+    key lengths against long contigs (score spacing coarser than 2/l_j) force it.  Both must give the exact distances."""
+    asm = synth.make("S1", 1500, seed=21)
+    res = _run(engine, asm, "5p6", 6, "tc")
+    addr = engine.uncertified_word(asm.n, asm.n, 0, 1088, 6, _lib.KB_KNN_TC)
+    assert int(engine.word_view(addr + 4).item()) == 0            # every Gram entry came out of its score
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, "5p6")
+    i_e, d_e = knn_oracle.knn_exact(counts, asm.key_len, 6, rows=range(0, asm.n, 300))
+    assert np.allclose(np.sqrt(d_e), res["knn_dist"][::300], rtol=1e-6, atol=0)
+    # long contigs (40 kb: sum c^2 ~ 2e6 < 2^24, unflagged), two rows with header keys of 50 000 characters
+    rng = np.random.default_rng(8)
+    n, length = 700, 40000
+    fam = rng.integers(0, 4, size=(35, length), dtype=np.uint8)
+    seqs = []
+    for r in range(n):
+        s = fam[r % 35].copy()
+        mut = rng.random(length) < 0.02 * (1 + r // 35)
+        s[mut] = rng.integers(0, 4, size=int(mut.sum()), dtype=np.uint8)
+        seqs.append(np.frombuffer(b"ACGT", dtype=np.uint8)[s])
+    bases = np.concatenate(seqs)
+    offsets = np.arange(n + 1, dtype=np.int64) * length
+    key_len = (700 + (np.arange(n) % 13)).astype(np.int32)
+    key_len[[0, 448]] = 50000                                     # their neighbours are rows with ordinary keys
+    res = profile_and_knn(engine, bases, offsets, key_len, "5p6", n_neighbors=6, impl=IMPLS["tc"])
+    addr = engine.uncertified_word(n, n, 0, 1088, 6, _lib.KB_KNN_TC)
+    assert int(engine.word_view(addr + 4).item()) > 0             # the operand-row path ran
+    counts, _ = ko.counts_mode(bases, offsets, "5p6")
+    prof = counts / key_len[:, None].astype(np.float64)
+    assert res["profile"].tobytes() == prof.tobytes()
+    ex = np.arange(0, n, 64)                                      # rows 0, 448 have the long keys
+    i_e, d_e = knn_oracle.knn_exact(counts, key_len, 6, rows=ex)
+    assert np.allclose(np.sqrt(d_e), res["knn_dist"][ex], rtol=1e-6, atol=0)
+    rows = np.arange(0, n, 3)
+    rep = knn_oracle.check_knn(res["knn_idx"][rows], res["knn_dist"][rows], knn_oracle.d2_fp64(prof, rows), rows=rows)
+    assert knn_oracle.parity_ok(rep), rep
