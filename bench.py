@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the supplementary blocks")
     ap.add_argument("--no-graph", action="store_true", help="enqueue the pass eagerly instead of replaying a CUDA graph")
     ap.add_argument("--shard-gen", action="store_true", help="each rank synthesises only its own row shard")
-    ap.add_argument("--big", default=None, help="comma list of contig counts for the sharded 5+6 / k=15 runs (default at N=8: 500000,1000000)")
+    ap.add_argument("--big", default=None, help="comma list of contig counts for the sharded 5+6 / k=15 runs (default at N=8: 500000,1000000; 0: none)")
     return ap.parse_args()
 
 
@@ -619,7 +619,7 @@ def run_ours(a):
                         "bytes_per_launch": dbytes, "launches": dn}
             elif rank == 0 and asm is not None:
                 extras["parity_sample"] = parity_sample_small(asm, kmer_size, all_idx[:n_total], all_dist[:n_total])
-            big = [int(x) for x in a.big.split(",")] if a.big else ([500000, 1000000] if world == 8 else [])
+            big = [int(x) for x in a.big.split(",") if int(x) > 0] if a.big else ([500000, 1000000] if world == 8 else [])
             for nb in big:
                 rec = big_run(torch, dist, eng, a, nb, rank, world, local, pk)
                 if rank == 0:

@@ -216,7 +216,9 @@ KB_API int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t
  * (fp16 in, fp32 accumulate: exact while counts <= 2048 and sqnorm < 2^24),
  * distances by norm expansion, per-row running top-k' in the epilogue
  * (k' = 8..64 for k <= 60).  Then K5 reranks the k' candidates exactly:
- *   d2 = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2     (fp64)
+ *   d2 = sum_c (c_ic*l_j - c_jc*l_i)^2 / (l_i*l_j)^2 = (l_j^2 n_i + l_i^2 n_j - 2 l_i l_j g_ij) / (l_i*l_j)^2   (fp64)
+ * with the integer Gram entry g_ij read back out of the candidate's fp32 score when exactly one integer maps to
+ * that score (the common case: no second pass over the operand rows), recomputed from the operand rows otherwise;
  * orders by (self first, d2, index) and CERTIFIES every row: with s = l_i*d2 - n_i/l_i the
  * exact score of its k-th neighbour, B the k'-th best fp32 score (every key that is not a
  * candidate scored >= B) and E = 2^-22*(Y^2 + 2cY), c^2 = n_i/l_i, Y = c + sqrt(c^2 + s), a bound
@@ -290,7 +292,9 @@ KB_API int kb_knn_plan_table(int sm_count, int impl, int64_t nq, int64_t nk, int
  *                    reads what they pushed for the previous pass
  *   kb_xchg_push     on `stream` (a side stream ordered after K3): wait until every peer is done with the
  *                    previous pass, copy this rank's shard of every region -- bytes [off + rank*shard_bytes,
- *                    +shard_bytes) -- into every peer's arena (copy engines), then arrive[rank] = epoch there
+ *                    +shard_bytes) -- into every peer's arena, then arrive[rank] = epoch there.  With 3+ ranks a
+ *                    kernel pushes (SM stores over NVLink, one destination at a time in the order K4 needs the
+ *                    shards; it runs next to the persistent K4 CTAs); with 2 ranks, or KB_XCHG_SM=0, the copy engines do
  *   kb_knn(..xchg..) sweeps the local shard first and waits for arrive[r] before the first key row of rank r
  *   kb_xchg_finish   on the context stream after K5: copy this rank's record (rec_words u32 at
  *                    rec_off + rank*rec_words*4) to every peer, raise the results flag everywhere and wait

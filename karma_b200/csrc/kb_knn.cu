@@ -25,6 +25,12 @@ namespace {
 
 struct Band { int64_t t_lo, cnt; };
 
+// What a piece costs on top of its tile visits (list set-up, cold first tile, descriptor and row-record loads, write-back),
+// in tile visits.  Measured on 50k x 1088: 132 visits in 2 pieces per CTA pair take 0.767 ms, 66 visits in 5.2 pieces 0.455 ms
+// against 5.56 us per visit for one long sweep: about 1.5 visits per piece.
+// (of 17 k-blocks; wider rows make a visit longer, not a piece dearer).
+inline double piece_cost(const KbKnnPlan& p) { return p.piece_cost; }
+
 struct Sched {
     std::vector<std::vector<KbPiece>> per_worker;
     std::vector<int32_t> slot_count;
@@ -33,10 +39,29 @@ struct Sched {
     double makespan = 0.0;
 };
 
-// unit (round r, group g): band (sd_g + r) % S, rotated to start at the diagonal tile when r == 0
+// unit (round r, group g).
+// All keys local (nq == nk): band (sd_g + r) % S, rotated to start at the diagonal tile when r == 0.
+// Query shard (the other shards arrive over NVLink in the order q+1, q+2, ..., q-1): the sweep of EVERY group is the
+// rotation of the key tiles that starts at the first tile lying fully inside the local shard and runs upwards with
+// wrap-around, cut into S equal bands -- so tiles are needed in exactly the order in which their shards land, and the tile
+// that straddles the start of the local shard (it needs rows of rank q-1, the LAST to arrive) comes last instead of
+// first.  Round 0 still starts at the group's own diagonal tile when that lies in the first band.
+// A piece visits tile(i) = (t_lo + ((i + shift) mod cnt)) mod n_tiles.
 inline void unit_of(const KbKnnPlan& p, int64_t q_row0, int S, int r, int64_t g, KbPiece* u) {
     int64_t td = (q_row0 + g * p.cl * p.bm) / p.bn;
     if (td >= p.n_tiles) td = p.n_tiles - 1;
+    if (p.shard) {
+        const int64_t n = p.n_tiles;
+        int64_t t_start = (q_row0 + p.bn - 1) / p.bn;                       // first tile fully inside the local rows ...
+        if ((t_start + 1) * p.bn > q_row0 + p.nq || t_start >= n) t_start = q_row0 / p.bn;   // ... if there is one
+        if (t_start >= n) t_start = n - 1;
+        const int64_t rho_lo = (n * r) / S, cnt = (n * (r + 1)) / S - rho_lo;   // equal bands of the rotated order
+        const int64_t rho_d = (td - t_start + n) % n;
+        u->group = (int32_t)g; u->slot = 0; u->t_lo = (int32_t)((t_start + rho_lo) % n); u->cnt = (int32_t)cnt;
+        u->shift = (rho_d >= rho_lo && rho_d < rho_lo + cnt) ? (int32_t)(rho_d - rho_lo) : 0;
+        u->i_lo = 0; u->i_cnt = (int32_t)cnt; u->pad = 0;
+        return;
+    }
     int sd = (int)((td * S) / p.n_tiles);
     while (sd + 1 < S && (p.n_tiles * (sd + 1)) / S <= td) ++sd;
     while (sd > 0 && (p.n_tiles * sd) / S > td) --sd;
@@ -64,7 +89,7 @@ void build_sched(const KbKnnPlan& p, int64_t q_row0, int S, int kind, Sched* out
                 u.slot = out->slot_count[g]++;
                 const int w = (int)(u_lin % W);
                 out->per_worker[w].push_back(u);
-                load[w] += u.i_cnt + 0.5;
+                load[w] += u.i_cnt + piece_cost(p);
             }
         } else {
             int64_t V = 0;
@@ -85,7 +110,7 @@ void build_sched(const KbKnnPlan& p, int64_t q_row0, int S, int kind, Sched* out
                     pc.slot = out->slot_count[g]++;
                     const int w = (j + rot) % W;
                     out->per_worker[w].push_back(pc);
-                    load[w] += take + 0.5;
+                    load[w] += take + piece_cost(p);
                     done += take; pos += take;
                 }
             }
@@ -137,6 +162,9 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, 
         else { p->bm = 64; p->bn = 64; }
         p->m_blocks = (nq + p->bm - 1) / p->bm;
         p->n_tiles = (nk + p->bn - 1) / p->bn;
+        p->nq = nq;
+        p->piece_cost = std::min(1.5, std::max(0.25, 1.5 * 1088.0 / (double)dp));
+        p->shard = (q_row0 > 0 || nq < nk) ? 1 : 0;
         if (impl == KB_KNN_TC) {
             int64_t cl = p->m_blocks >= 2 ? 2 : 1;
             if (const char* f = getenv("KB_KNN_CLUSTER")) {         // experiments only: 1, 2 or 4 CTAs share every key tile
@@ -158,7 +186,7 @@ int kb_knn_plan(int sm_count, int impl, int64_t nq, int64_t nk, int64_t q_row0, 
             if (const char* f = getenv("KB_KNN_L2_MB")) l2_mb = atof(f);   // experiments only
             const double key_bytes = (double)nk * dp * 2.0;
             const bool sync_only = key_bytes > l2_mb * 1e6;
-            const bool shard = q_row0 > 0 || nq < nk;                // arrival order: at least 4 bands
+            const bool shard = p->shard != 0;                        // arrival order: at least 4 bands
             const int min_bands[2] = {key_bytes > 0.5 * l2_mb * 1e6 ? 2 : (shard ? 4 : 1),
                                       (key_bytes > 0.5 * l2_mb * 1e6 || shard) ? 4 : 1};
             choose_sched(*p, q_row0, min_bands, sync_only, &s, &S, &kind);
@@ -626,12 +654,29 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 // ---------------------------------------------------------------------------
 // K4x: exact side path.  Rows whose counts do not fit the tensor path exactly
 // (flags bit0: a count > 2048, bit1: sum c^2 >= 2^24 -- contigs beyond ~130 kb, long
-// homopolymers) are "flagged": masked out of the Gram kernel and handled here in fp64
-// from their true u32 counts.  One CTA per query row:
+// homopolymers) are "flagged": masked out of the Gram kernel and handled here from their
+// true u32 counts (exact 64-bit integer Gram entries, fp64 only for the final d2).  One CTA per query row:
 //   flagged query   -> exact d2 to EVERY key
 //   unflagged query -> exact d2 to every FLAGGED key
 // and the KP best go to K5 as extra candidates.
 // ---------------------------------------------------------------------------
+// d2 = (l_j^2 n_i + l_i^2 n_j - 2 l_i l_j g) / (l_i l_j)^2 from the exact integers n_i, n_j (sum c^2) and g (sum c_i c_j).
+// While every term stays below 2^51 the numerator is exact in fp64 (one rounding, the division); beyond that (key
+// lengths in the thousands against contigs of hundreds of kb) it is formed in 128-bit integers first.
+__device__ __forceinline__ double kb_d2_from_gram(double ni, int32_t li, double nj, int32_t lj, unsigned long long g) {
+    const double dli = (double)li, dlj = (double)lj;
+    const double a = dlj * dlj * ni, b = dli * dli * nj, c = 2.0 * (dli * dlj) * (double)g;
+    const double den = (dli * dlj) * (dli * dlj);
+    const double lim = 2251799813685248.0;                    // 2^51
+    if (a < lim && b < lim && c < lim) return (a + b - c) / den;
+    const unsigned __int128 A = (unsigned __int128)((unsigned long long)lj * (unsigned long long)lj) * (unsigned long long)ni;
+    const unsigned __int128 B = (unsigned __int128)((unsigned long long)li * (unsigned long long)li) * (unsigned long long)nj;
+    const unsigned __int128 C = (unsigned __int128)(2ull * (unsigned long long)li * (unsigned long long)lj) * g;
+    const unsigned __int128 num = A + B >= C ? A + B - C : 0;               // Cauchy-Schwarz: never negative
+    const double hi = (double)(unsigned long long)(num >> 64), lo = (double)(unsigned long long)num;
+    return (hi * 18446744073709551616.0 + lo) / den;
+}
+
 __device__ __forceinline__ int find_slot(const int32_t* __restrict__ rows, int n, int32_t row) {
     int lo = 0, hi = n - 1;
     while (lo <= hi) {
@@ -669,36 +714,50 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
         }
         for (int e = lane; e < KP; e += 32) { wl_d[warp][e] = DINF; wl_i[warp][e] = -1; }
         __syncthreads();
-        const double lq = (double)mq.key_len;
         const int64_t n_keys = q_flagged ? nk : (int64_t)n_flag;
         double thr = DINF; int pos = 0;                        // lane 0: worst entry of this warp's list
+        const uint4* q4 = reinterpret_cast<const uint4*>(qrow);
         for (int64_t t = warp; t < n_keys; t += 8) {
             const int32_t j = q_flagged ? (int32_t)t : flag_rows[t];
             const kb_rowmeta mj = rowmeta[j];
             if (mj.flags & 8) continue;                        // padding row of a multi-rank gather
-            const double lj = (double)mj.key_len;
-            double acc = 0.0;
+            // exact integer Gram entry g = sum_c a_c*b_c (u32 x u32 -> u64 multiply-adds; a 200 kb homopolymer against
+            // itself stays below 2^36): one integer instruction per column instead of an fp64 difference and square
+            unsigned long long g = 0;
             if (mj.flags & 3) {
-                const int slot = find_slot(flag_rows, n_flag, j);
-                const uint32_t* krow = flag_counts + (int64_t)slot * ld_fc;
-                for (int c = lane; c < dp; c += 32) {
-                    const double b = (slot >= 0 && c < fc_cols) ? (double)krow[c] : 0.0;
-                    const double d = (double)qrow[c] * lj - b * lq;
-                    acc = fma(d, d, acc);
+                const int slot = q_flagged ? find_slot(flag_rows, n_flag, j) : (int)t;
+                if (slot >= 0) {
+                    const uint32_t* krow = flag_counts + (int64_t)slot * ld_fc;
+                    const int nc = fc_cols < dp ? fc_cols : dp;
+                    if ((ld_fc & 3) == 0 && (reinterpret_cast<uintptr_t>(flag_counts) & 15) == 0) {
+                        const uint4* k4 = reinterpret_cast<const uint4*>(krow);
+                        const int n4 = nc >> 2;
+                        for (int c = lane; c < n4; c += 32) {
+                            const uint4 b = __ldg(k4 + c); const uint4 a = q4[c];
+                            g += (unsigned long long)a.x * b.x; g += (unsigned long long)a.y * b.y;
+                            g += (unsigned long long)a.z * b.z; g += (unsigned long long)a.w * b.w;
+                        }
+                        for (int c = (n4 << 2) + lane; c < nc; c += 32) g += (unsigned long long)qrow[c] * __ldg(krow + c);
+                    } else {
+                        for (int c = lane; c < nc; c += 32) g += (unsigned long long)qrow[c] * __ldg(krow + c);
+                    }
                 }
             } else {
-                const __half* krow = op + (int64_t)j * ld;
-                for (int c = 2 * lane; c < dp; c += 64) {
-                    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(krow + c));
-                    const double d0 = (double)qrow[c] * lj - (double)fb.x * lq;
-                    const double d1 = (double)qrow[c + 1] * lj - (double)fb.y * lq;
-                    acc = fma(d0, d0, acc);
-                    acc = fma(d1, d1, acc);
+                const uint4* k8 = reinterpret_cast<const uint4*>(op + (int64_t)j * ld);   // 8 fp16 counts (exact integers <= 2048)
+                for (int c = lane; c < (dp >> 3); c += 32) {
+                    const uint4 b = __ldg(k8 + c);
+                    const uint4 a0 = q4[2 * c], a1 = q4[2 * c + 1];
+                    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+                    const float2 b0 = __half22float2(hb[0]), b1 = __half22float2(hb[1]), b2 = __half22float2(hb[2]), b3 = __half22float2(hb[3]);
+                    g += (unsigned long long)a0.x * (uint32_t)b0.x; g += (unsigned long long)a0.y * (uint32_t)b0.y;
+                    g += (unsigned long long)a0.z * (uint32_t)b1.x; g += (unsigned long long)a0.w * (uint32_t)b1.y;
+                    g += (unsigned long long)a1.x * (uint32_t)b2.x; g += (unsigned long long)a1.y * (uint32_t)b2.y;
+                    g += (unsigned long long)a1.z * (uint32_t)b3.x; g += (unsigned long long)a1.w * (uint32_t)b3.y;
                 }
             }
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
             if (lane == 0) {
-                const double d2 = acc / ((lq * lj) * (lq * lj));
+                const double d2 = kb_d2_from_gram(mq.sqnorm, mq.key_len, mj.sqnorm, mj.key_len, g);
                 if (d2 < thr || (d2 == thr && wl_i[warp][pos] < 0)) {
                     wl_d[warp][pos] = d2; wl_i[warp][pos] = j;
                     double m = -1.0; int mp = 0;

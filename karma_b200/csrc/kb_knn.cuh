@@ -8,9 +8,10 @@
 
 // One piece of work of the tensor kernel: query-block group `group` (CL adjacent 128-row blocks, one
 // per CTA of the cluster) against the key tiles tile(i), i in [i_lo, i_lo + i_cnt), of the sweep
-//     tile(i) = t_lo + ((i + shift) mod cnt)
-// (a band of `cnt` key tiles starting at t_lo, rotated so that the band holding the group's diagonal
-// starts AT the diagonal).  The running top-KP list of every row is written to candidate slot `slot`.
+//     tile(i) = (t_lo + ((i + shift) mod cnt)) mod n_tiles
+// (a band of `cnt` key tiles starting at t_lo -- for a query shard it may wrap round the end of the key set --
+// rotated so that the band holding the group's diagonal starts AT the diagonal).  The running top-KP list of
+// every row is written to candidate slot `slot`.
 struct KbPiece {
     int32_t group, slot, t_lo, cnt, shift, i_lo, i_cnt, pad;
 };
@@ -25,6 +26,8 @@ struct KbKnnPlan {
     int bm, bn;          // tile shape
     int64_t m_blocks;    // ceil(nq / bm)
     int64_t n_tiles;     // ceil(nk / bn)
+    int64_t nq;          // query rows
+    int shard;           // the queries are a row shard of the keys (the other shards arrive over NVLink)
     int cl;              // tensor path: CTAs per cluster sharing one key-tile stream (1, 2 or 4)
     int64_t groups;      // ceil(m_blocks / cl)
     int workers;         // tensor path: clusters launched
@@ -32,7 +35,8 @@ struct KbKnnPlan {
     int bands;           // tensor path: S
     int sched_kind;      // 0: whole units dealt round-robin, 1: every band cut into equal ranges
     int64_t n_pieces;
-    double makespan;     // tile visits (+0.5 per piece) of the busiest worker
+    double piece_cost;   // what a piece costs on top of its tile visits, in tile visits (model)
+    double makespan;     // tile visits (+ piece_cost per piece) of the busiest worker
     // workspace offsets (bytes)
     int64_t off_score, off_idx, off_rowthr, off_xidx, off_xd2, off_uncert, total;
 };

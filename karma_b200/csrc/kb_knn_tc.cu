@@ -140,6 +140,7 @@ struct TcParams {
     int64_t nk, q_row0, nq;
     int slots;                        // candidate lists per query row (stride of cand_*)
     int k_blocks;                     // Dp / 64
+    int32_t n_tiles;                  // ceil(nk / BN)
     const kb_rowmeta* rowmeta;
     float* cand_score;
     int32_t* cand_idx;
@@ -158,10 +159,12 @@ __device__ __forceinline__ KbPiece load_piece(const KbPiece* p) {
     pc.group = a.x; pc.slot = a.y; pc.t_lo = a.z; pc.cnt = a.w; pc.shift = b.x; pc.i_lo = b.y; pc.i_cnt = b.z; pc.pad = 0;
     return pc;
 }
-__device__ __forceinline__ int64_t piece_tile(const KbPiece& pc, int i) {
+__device__ __forceinline__ int64_t piece_tile(const KbPiece& pc, int i, int32_t n_tiles) {
     int t = i + pc.shift;
     if (t >= pc.cnt) t -= pc.cnt;
-    return (int64_t)pc.t_lo + t;
+    t += pc.t_lo;
+    if (t >= n_tiles) t -= n_tiles;                          // a shard's band may wrap round the end of the key set
+    return (int64_t)t;
 }
 
 // Wait (bounded) until the shard of the rank owning key row `row` has arrived.  `seen` caches the answer.
@@ -258,7 +261,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
                 const KbPiece pc = load_piece(p.pieces + pi);
                 const int32_t arow = (int32_t)(p.q_row0 + ((int64_t)pc.group * CL + cta_rank) * BM);
                 for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
-                    const int32_t brow = (int32_t)(piece_tile(pc, i) * BN);
+                    const int32_t brow = (int32_t)(piece_tile(pc, i, p.n_tiles) * BN);
                     if (p.arrive) {
                         wait_row_arrived(p, epoch, brow, seen, 1);
                         wait_row_arrived(p, epoch, (int64_t)brow + BN - 1, seen, 1);
@@ -333,7 +336,7 @@ k4_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensor
             list.init(r);
             float thr = __int_as_float(0x7f800000);          // min(own KP-th best, row_thr): the prune bound
             for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
-                const int64_t n0 = piece_tile(pc, i) * BN;
+                const int64_t n0 = piece_tile(pc, i, p.n_tiles) * BN;
                 // stage this tile's key records (all 128 epilogue threads); refresh the shared bound
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (p.arrive) { wait_row_arrived(p, epoch, n0 + et, seen, 5); wait_row_arrived(p, epoch, n0 + et + 128, seen, 5); }
@@ -511,7 +514,7 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                 const KbPiece pc = load_piece(p.pieces + pi);
                 const int32_t arow = (int32_t)(p.q_row0 + ((int64_t)pc.group * 2 + cta_rank) * BM);
                 for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
-                    const int32_t brow = (int32_t)(piece_tile(pc, i) * BN) + 128 * cta_rank;   // my half of the key tile
+                    const int32_t brow = (int32_t)(piece_tile(pc, i, p.n_tiles) * BN) + 128 * cta_rank;   // my half of the key tile
                     if (p.arrive) {
                         wait_row_arrived(p, epoch, brow, seen, 11);
                         wait_row_arrived(p, epoch, (int64_t)brow + 127, seen, 11);
@@ -595,7 +598,7 @@ k4_tc2(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                 cnt = 0;
             };
             for (int i = pc.i_lo; i < pc.i_lo + pc.i_cnt; ++i) {
-                const int64_t n0 = piece_tile(pc, i) * BN;
+                const int64_t n0 = piece_tile(pc, i, p.n_tiles) * BN;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (p.arrive) { wait_row_arrived(p, epoch, n0 + et, seen, 15); wait_row_arrived(p, epoch, n0 + et + 128, seen, 15); }
                 cm_s[et] = kb_load_cm(p.rowmeta, n0 + et, p.nk);
@@ -794,6 +797,7 @@ int kb_knn_tc_launch(kb_ctx* ctx, const KbKnnPlan& p, const KbTcArgs& a) {
     prm.nk = a.nk; prm.q_row0 = a.q_row0; prm.nq = a.nq;
     prm.slots = p.slots;
     prm.k_blocks = a.d_cols_padded / BK;
+    prm.n_tiles = (int32_t)((a.nk + BN - 1) / BN);
     prm.rowmeta = a.d_rowmeta;
     prm.cand_score = a.cand_score; prm.cand_idx = a.cand_idx; prm.row_thr = a.row_thr;
     prm.pieces = a.pieces; prm.piece_start = a.piece_start;

@@ -889,6 +889,7 @@ class PassPlan:
         self.graph = None
         self._want_graph = bool(graph)
         self._io = None                                         # host-to-host pass (bind_host / run_host)
+        self._marks = None                                      # diagnostics: [(name, event)] filled by an eager enqueue
         self.host = None
 
     # ---- exchange set-up (once) -----------------------------------------------------------
@@ -989,6 +990,14 @@ class PassPlan:
         e._bind_stream()
         main = torch.cuda.current_stream(e.device)
         io = self._io if host_io else None
+        marks = self._marks
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(main)
+                marks.append((name, ev))
+        mark("start")
         if io is not None:
             fork = torch.cuda.Event()
             fork.record(main)
@@ -1008,6 +1017,7 @@ class PassPlan:
         if self.x is not None:
             check(lib.kb_xchg_begin(self.x))
         self.rec.zero_()                                        # flags, uncertified rows and the presence vector
+        mark("begin")
         n_alloc = self.per if self.x is not None else self.n
         q0 = self.q_row0
         # K1+K3 fused: the histogram of every contig goes straight to its profile / operand / record rows
@@ -1028,19 +1038,27 @@ class PassPlan:
                 io["down"].wait_event(ev)
                 with torch.cuda.stream(io["down"]):
                     io["h_profile"][lo:hi].copy_(self.profile[lo:hi], non_blocking=True)
+        mark("count")
         if self.x is not None:
             ev = torch.cuda.Event()
             ev.record(main)
             self.side.wait_event(ev)
             check(lib.kb_xchg_push(self.x, c_void_p(self.side.cuda_stream), 2, self._regions[0], self._regions[1]))
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(self.side)
+                marks.append(("push_done(side)", ev))
         if self.want_knn and self.n:
             check(lib.kb_knn(e.ctx, self.impl, self.k, ptr(self.operand_all), self.dp, self.dp, ptr(self.rowmeta_all),
                              self.nk, self.q_row0, self.n, None, None, 0, 0, 0, ptr(self.idx), ptr(self.dist), None,
                              ptr(self.ws), self.ws.numel(), byref(self._xchg) if self.x is not None else None))
             self.rec[1:2].copy_(self._unc, non_blocking=True)
+        mark("knn")
         if self.x is not None:
             check(lib.kb_xchg_finish(self.x, self._lay["rec"], self.rec_words))
+            mark("finish")
             main.wait_stream(self.side)
+        mark("end")
         if io is not None:
             # small results last: they queue behind the profile rows on the D2H copy engine and must not hold back K4
             if self.want_knn and self.n:

@@ -169,9 +169,9 @@ def test_knn_piece_table_covers_every_tile_once(lib, nq, nk, q0, dp, k):
     for g, slot, t_lo, cnt, shift, i_lo, i_cnt, _ in pieces:
         assert (g, slot) not in seen and 0 <= slot < slots[g] <= info["slots"]
         seen.add((g, slot))
-        assert 0 <= i_lo and i_lo + i_cnt <= cnt and i_cnt >= 1 and 0 <= shift < cnt
+        assert 0 <= i_lo and i_lo + i_cnt <= cnt and i_cnt >= 1 and 0 <= shift < cnt and 0 <= t_lo < n_tiles
         i = np.arange(i_lo, i_lo + i_cnt) + shift
-        cover[g, np.where(i >= cnt, i - cnt, i) + t_lo] += 1
+        cover[g, (np.where(i >= cnt, i - cnt, i) + t_lo) % n_tiles] += 1
     assert (cover == 1).all()
     assert info["slots"] * info["kp"] <= 512
     assert start[0] == 0 and start[-1] == len(pieces) and (np.diff(start) >= 0).all()
