@@ -230,7 +230,9 @@ KB_API int kb_rowmeta_flags_or(kb_ctx* ctx, const kb_rowmeta* d_rowmeta, int64_t
  * d_dist receives sqrt(d2) as float (UMAP's knn_dists), d_d2 (nullable) the fp64 squared
  * distances.
  * Exact side path (K4x): rows whose flags bit0/bit1 are set cannot be scored exactly by
- * the tensor path; they are masked there and handled in fp64 from their true counts:
+ * the tensor path; they are masked there and handled from their true counts (exact 64-bit integer
+ * Gram entries): an ordinary query gets its exact distances to every flagged key as extra candidates;
+ * a flagged QUERY is always listed for kb_knn_fixup (exact distances to all keys):
  *  d_flag_rows   int32[n_flag]  ascending key-row indices of ALL flagged rows
  *  d_flag_counts uint32[n_flag*ld_flag_counts]  their count rows (flag_cols columns)
  * (both NULL / 0 when no row is flagged).

@@ -41,11 +41,11 @@ struct Sched {
 
 // unit (round r, group g).
 // All keys local (nq == nk): band (sd_g + r) % S, rotated to start at the diagonal tile when r == 0.
-// Query shard (the other shards arrive over NVLink in the order q+1, q+2, ..., q-1): the sweep of EVERY group is the
-// rotation of the key tiles that starts at the first tile lying fully inside the local shard and runs upwards with
-// wrap-around, cut into S equal bands -- so tiles are needed in exactly the order in which their shards land, and the tile
-// that straddles the start of the local shard (it needs rows of rank q-1, the LAST to arrive) comes last instead of
-// first.  Round 0 still starts at the group's own diagonal tile when that lies in the first band.
+// Query shard (the other shards arrive over NVLink in the order q+1, q+2, ..., q-1): the sweep of a group is a
+// rotation of the key tiles that starts inside the local shard (at the group's diagonal tile, or earlier, see LEAD) and
+// runs upwards with wrap-around, cut into S equal bands -- so tiles are needed in exactly the order in which their
+// shards land, and the tile that straddles the start of the local shard (it needs rows of rank q-1, the LAST to
+// arrive) comes after all the shards instead of first.
 // A piece visits tile(i) = (t_lo + ((i + shift) mod cnt)) mod n_tiles.
 inline void unit_of(const KbKnnPlan& p, int64_t q_row0, int S, int r, int64_t g, KbPiece* u) {
     int64_t td = (q_row0 + g * p.cl * p.bm) / p.bn;
@@ -55,10 +55,18 @@ inline void unit_of(const KbKnnPlan& p, int64_t q_row0, int S, int r, int64_t g,
         int64_t t_start = (q_row0 + p.bn - 1) / p.bn;                       // first tile fully inside the local rows ...
         if ((t_start + 1) * p.bn > q_row0 + p.nq || t_start >= n) t_start = q_row0 / p.bn;   // ... if there is one
         if (t_start >= n) t_start = n - 1;
-        const int64_t rho_lo = (n * r) / S, cnt = (n * (r + 1)) / S - rho_lo;   // equal bands of the rotated order
-        const int64_t rho_d = (td - t_start + n) % n;
-        u->group = (int32_t)g; u->slot = 0; u->t_lo = (int32_t)((t_start + rho_lo) % n); u->cnt = (int32_t)cnt;
-        u->shift = (rho_d >= rho_lo && rho_d < rho_lo + cnt) ? (int32_t)(rho_d - rho_lo) : 0;
+        // A group starts at its own diagonal tile (its rows' nearest neighbours are mostly there: tight bounds from the
+        // first tile on) unless that leaves fewer than LEAD local tiles before the first tile of the next shard is due --
+        // then it starts that much earlier, so that nobody waits for the first arrival.
+        constexpr int64_t LEAD = 32;
+        int64_t local = (q_row0 + p.nq) / p.bn - t_start;                   // tiles fully inside the local rows
+        if (local < 1) local = 1;
+        int64_t off_d = (td - t_start + n) % n;                             // the diagonal in rotated coordinates
+        if (off_d >= local) off_d = (off_d == n - 1) ? 0 : local - 1;       // (it is one of the two straddling tiles)
+        const int64_t o = std::min<int64_t>(off_d, std::max<int64_t>(0, local - LEAD));
+        const int64_t rho_lo = (n * r) / S, cnt = (n * (r + 1)) / S - rho_lo;   // equal bands of the group's rotated order
+        u->group = (int32_t)g; u->slot = 0; u->t_lo = (int32_t)((t_start + o + rho_lo) % n); u->cnt = (int32_t)cnt;
+        u->shift = 0;
         u->i_lo = 0; u->i_cnt = (int32_t)cnt; u->pad = 0;
         return;
     }
@@ -626,7 +634,9 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
     //   Flagged keys only come through the extras (exact): if that list is full, the k-th neighbour must
     //   not be farther than its last entry.
     if (lane == 0) {
-        bool ok = true;
+        // a flagged QUERY needs exact distances to every key: that is the exact pass (K6), which spreads one row over
+        // many CTAs -- K4x only serves ordinary queries (their distances to the few flagged keys)
+        bool ok = !q_flagged;
         if (!q_flagged) {
             if (n_valid < k) ok = (m_last == INF);
             else if (m_last != INF) {
@@ -656,9 +666,8 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 // (flags bit0: a count > 2048, bit1: sum c^2 >= 2^24 -- contigs beyond ~130 kb, long
 // homopolymers) are "flagged": masked out of the Gram kernel and handled here from their
 // true u32 counts (exact 64-bit integer Gram entries, fp64 only for the final d2).  One CTA per query row:
-//   flagged query   -> exact d2 to EVERY key
-//   unflagged query -> exact d2 to every FLAGGED key
-// and the KP best go to K5 as extra candidates.
+//   unflagged query -> exact d2 to every FLAGGED key; the KP best go to K5 as extra candidates
+//   flagged query   -> nothing here: K5 lists it for the exact pass over all keys (K6, kb_knn_fixup)
 // ---------------------------------------------------------------------------
 // d2 = (l_j^2 n_i + l_i^2 n_j - 2 l_i l_j g) / (l_i l_j)^2 from the exact integers n_i, n_j (sum c^2) and g (sum c_i c_j).
 // While every term stays below 2^51 the numerator is exact in fp64 (one rounding, the division); beyond that (key
@@ -706,26 +715,25 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
         const bool q_flagged = (mq.flags & 3) != 0;
         __syncthreads();
         if (q_flagged) {
-            const int slot = find_slot(flag_rows, n_flag, self);
-            for (int c = threadIdx.x; c < dp; c += 256)
-                qrow[c] = (slot >= 0 && c < fc_cols) ? flag_counts[(int64_t)slot * ld_fc + c] : 0u;
-        } else {
-            for (int c = threadIdx.x; c < dp; c += 256) qrow[c] = (uint32_t)__half2float(op[(int64_t)self * ld + c]);
+            // K5 lists every flagged query for the exact pass over all keys (K6); nothing to propose here
+            for (int e = threadIdx.x; e < KP; e += 256) { extra_idx[q * KP + e] = -1; extra_d2[q * KP + e] = DINF; }
+            continue;
         }
+        for (int c = threadIdx.x; c < dp; c += 256) qrow[c] = (uint32_t)__half2float(op[(int64_t)self * ld + c]);
         for (int e = lane; e < KP; e += 32) { wl_d[warp][e] = DINF; wl_i[warp][e] = -1; }
         __syncthreads();
-        const int64_t n_keys = q_flagged ? nk : (int64_t)n_flag;
+        const int64_t n_keys = (int64_t)n_flag;
         double thr = DINF; int pos = 0;                        // lane 0: worst entry of this warp's list
         const uint4* q4 = reinterpret_cast<const uint4*>(qrow);
         for (int64_t t = warp; t < n_keys; t += 8) {
-            const int32_t j = q_flagged ? (int32_t)t : flag_rows[t];
+            const int32_t j = flag_rows[t];
             const kb_rowmeta mj = rowmeta[j];
             if (mj.flags & 8) continue;                        // padding row of a multi-rank gather
             // exact integer Gram entry g = sum_c a_c*b_c (u32 x u32 -> u64 multiply-adds; a 200 kb homopolymer against
             // itself stays below 2^36): one integer instruction per column instead of an fp64 difference and square
             unsigned long long g = 0;
             if (mj.flags & 3) {
-                const int slot = q_flagged ? find_slot(flag_rows, n_flag, j) : (int)t;
+                const int slot = (int)t;                       // keys are the flagged rows, in flag_rows order
                 if (slot >= 0) {
                     const uint32_t* krow = flag_counts + (int64_t)slot * ld_fc;
                     const int nc = fc_cols < dp ? fc_cols : dp;
@@ -845,16 +853,21 @@ k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta*
         for (int i = 0; i < K6_QB; ++i) any_f |= qf[i];
         if (!pad) {
             if (any_f) {
-                // fp64 from the true counts: sum_c (a_c*lj - b_c*lq)^2
+                // a flagged row is involved: exact 64-bit integer Gram entries from the true counts
+                unsigned long long gi[K6_QB];
+#pragma unroll
+                for (int i = 0; i < K6_QB; ++i) gi[i] = 0ull;
                 const int slot = kf ? find_slot(flag_rows, n_flag, (int32_t)j) : -1;
                 for (int c = lane; c < dp; c += 32) {
-                    const double b = kf ? ((slot >= 0 && c < fc_cols) ? (double)flag_counts[(int64_t)slot * ld_fc + c] : 0.0)
-                                        : (double)__half2float(op[j * ld + c]);
+                    const uint32_t b = kf ? ((slot >= 0 && c < fc_cols) ? flag_counts[(int64_t)slot * ld_fc + c] : 0u)
+                                          : (uint32_t)__half2float(op[j * ld + c]);
 #pragma unroll
-                    for (int i = 0; i < K6_QB; ++i) {
-                        const double d = (double)qs[i * dp + c] * lj - b * lqs[i];
-                        acc[i] = fma(d, d, acc[i]);
-                    }
+                    for (int i = 0; i < K6_QB; ++i) gi[i] += (unsigned long long)__float2uint_rn(qs[i * dp + c]) * b;
+                }
+#pragma unroll
+                for (int i = 0; i < K6_QB; ++i) {
+                    for (int o = 16; o > 0; o >>= 1) gi[i] += __shfl_xor_sync(0xffffffffu, gi[i], o);
+                    acc[i] = kb_d2_from_gram(nqs[i], (int32_t)lqs[i], mj.sqnorm, mj.key_len, gi[i]);   // d2 itself
                 }
             } else {
                 // unflagged x unflagged: the fp32 dot product is the exact integer Gram entry
@@ -879,9 +892,11 @@ k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta*
                 for (int i = 0; i < K6_QB; ++i) acc[i] = (double)g[i];
             }
         }
+        if (!any_f) {
 #pragma unroll
-        for (int i = 0; i < K6_QB; ++i)
-            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            for (int i = 0; i < K6_QB; ++i)
+                for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < K6_QB; ++i) {
@@ -889,7 +904,7 @@ k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta*
                 double d2;
                 if (pad) d2 = DINF;
                 else if ((int32_t)j == selfs[i]) d2 = -1.0;                   // the point itself sorts first
-                else if (any_f) d2 = acc[i] / ((lqs[i] * lj) * (lqs[i] * lj));
+                else if (any_f) d2 = acc[i];
                 else {
                     const double num = lj * lj * nqs[i] + lqs[i] * lqs[i] * mj.sqnorm - 2.0 * (lj * lqs[i]) * acc[i];
                     d2 = num / ((lqs[i] * lj) * (lqs[i] * lj));

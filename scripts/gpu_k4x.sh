@@ -1,9 +1,9 @@
 #!/bin/bash
-# single GPU: kNN + count + plan tests (K4x with integer Gram entries, rotated shard sweeps), S3 general path, shard K4 timings
+# single GPU: kNN tests (K4x / K6 with integer Gram entries), S3 general path
 set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1; echo "build rc=$?"
-timeout 1200 python -m pytest tests/test_gpu_knn.py tests/test_gpu_plan.py tests/test_gpu_count.py -m gpu -q -x 2>&1 | tail -25 > gpurun_out/pytest_knn.log; echo "tests rc=${PIPESTATUS[0]}"
+timeout 1200 python -m pytest tests/test_gpu_knn.py tests/test_gpu_count.py -m gpu -q -x 2>&1 | tail -25 > gpurun_out/pytest_knn.log; echo "tests rc=${PIPESTATUS[0]}"
 tail -4 gpurun_out/pytest_knn.log
 timeout 600 python scripts/bench_config5.py 200000 S3 > gpurun_out/bench_config5_s3.jsonl 2> gpurun_out/bench_config5_s3.err; echo "config5 S3 rc=$?"
 python - <<PY
@@ -12,4 +12,3 @@ for l in open("gpurun_out/bench_config5_s3.jsonl"):
     d=json.loads(l); print({k:d.get(k) for k in ("ms_per_pass","general_path_ms","general_path_first_call_ms","flagged_rows","general_path_stage_ms")})
 PY
 tail -3 gpurun_out/bench_config5_s3.err
-timeout 300 python scripts/exp_k4.py 5p6 2 1,2,4,8 2>&1 | grep "K4 "
