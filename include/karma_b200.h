@@ -294,9 +294,9 @@ KB_API int kb_knn_plan_table(int sm_count, int impl, int64_t nq, int64_t nk, int
  *                    reads what they pushed for the previous pass
  *   kb_xchg_push     on `stream` (a side stream ordered after K3): wait until every peer is done with the
  *                    previous pass, copy this rank's shard of every region -- bytes [off + rank*shard_bytes,
- *                    +shard_bytes) -- into every peer's arena, then arrive[rank] = epoch there.  With 3+ ranks a
- *                    kernel pushes (SM stores over NVLink, one destination at a time in the order K4 needs the
- *                    shards; it runs next to the persistent K4 CTAs); with 2 ranks, or KB_XCHG_SM=0, the copy engines do
+ *                    +shard_bytes) -- into every peer's arena (copy engines, three peers at a time, nearest-following
+ *                    rank first), then arrive[rank] = epoch there.  KB_XCHG_SM=1 pushes with a kernel instead (SM stores
+ *                    over NVLink next to the persistent K4 CTAs; measured slower at 8 ranks)
  *   kb_knn(..xchg..) sweeps the local shard first and waits for arrive[r] before the first key row of rank r
  *   kb_xchg_finish   on the context stream after K5: copy this rank's record (rec_words u32 at
  *                    rec_off + rank*rec_words*4) to every peer, raise the results flag everywhere and wait

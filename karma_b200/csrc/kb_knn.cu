@@ -665,7 +665,7 @@ k5_merge_rerank(const __half* __restrict__ op, int64_t ld, int32_t dp,
 // K4x: exact side path.  Rows whose counts do not fit the tensor path exactly
 // (flags bit0: a count > 2048, bit1: sum c^2 >= 2^24 -- contigs beyond ~130 kb, long
 // homopolymers) are "flagged": masked out of the Gram kernel and handled here from their
-// true u32 counts (exact 64-bit integer Gram entries, fp64 only for the final d2).  One CTA per query row:
+// true u32 counts (exact 64-bit integer Gram entries, fp64 only for the final d2).  Four query rows per CTA:
 //   unflagged query -> exact d2 to every FLAGGED key; the KP best go to K5 as extra candidates
 //   flagged query   -> nothing here: K5 lists it for the exact pass over all keys (K6, kb_knn_fixup)
 // ---------------------------------------------------------------------------
@@ -697,80 +697,91 @@ __device__ __forceinline__ int find_slot(const int32_t* __restrict__ rows, int n
     return -1;
 }
 
-template <int KP>
+// QB: query rows per CTA (4: every flagged key row read serves four queries; 1 when four rows of dp counts do not fit
+// the shared memory, i.e. beyond ~10k columns)
+template <int KP, int QB>
 __global__ void __launch_bounds__(256)
 k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta* __restrict__ rowmeta,
           int64_t nk, int64_t q_row0, int64_t nq,
           const int32_t* __restrict__ flag_rows, const uint32_t* __restrict__ flag_counts, int64_t ld_fc,
           int32_t fc_cols, int32_t n_flag,
           int32_t* __restrict__ extra_idx, double* __restrict__ extra_d2) {
-    extern __shared__ __align__(16) uint32_t qrow[];          // dp exact counts of the query row
-    __shared__ double wl_d[8][KP];
-    __shared__ int32_t wl_i[8][KP];
+    extern __shared__ __align__(16) uint32_t qrows[];         // QB x dp exact counts of the query rows
+    __shared__ double wl_d[8][QB][KP];                        // per warp and query: running KP best flagged keys
+    __shared__ int32_t wl_i[8][QB][KP];
+    __shared__ double q_n[QB]; __shared__ int32_t q_l[QB]; __shared__ int32_t q_ok[QB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double DINF = __longlong_as_double(0x7ff0000000000000LL);
-    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
-        const int32_t self = (int32_t)(q_row0 + q);
-        const kb_rowmeta mq = rowmeta[self];
-        const bool q_flagged = (mq.flags & 3) != 0;
+    const bool vec = (ld_fc & 3) == 0 && (reinterpret_cast<uintptr_t>(flag_counts) & 15) == 0;
+    const int nc = fc_cols < dp ? fc_cols : dp;
+    const int n4 = vec ? (nc >> 2) : 0;
+    for (int64_t qb = (int64_t)blockIdx.x * QB; qb < nq; qb += (int64_t)gridDim.x * QB) {
         __syncthreads();
-        if (q_flagged) {
-            // K5 lists every flagged query for the exact pass over all keys (K6); nothing to propose here
-            for (int e = threadIdx.x; e < KP; e += 256) { extra_idx[q * KP + e] = -1; extra_d2[q * KP + e] = DINF; }
-            continue;
+        if (threadIdx.x < QB) {
+            const int64_t q = qb + threadIdx.x;
+            int ok = 0;
+            if (q < nq) {
+                const kb_rowmeta mq = rowmeta[q_row0 + q];
+                // a flagged QUERY is listed by K5 for the exact pass over all keys (K6); nothing to propose here
+                ok = (mq.flags & 3) == 0;
+                q_n[threadIdx.x] = mq.sqnorm; q_l[threadIdx.x] = mq.key_len;
+            }
+            q_ok[threadIdx.x] = ok;
         }
-        for (int c = threadIdx.x; c < dp; c += 256) qrow[c] = (uint32_t)__half2float(op[(int64_t)self * ld + c]);
-        for (int e = lane; e < KP; e += 32) { wl_d[warp][e] = DINF; wl_i[warp][e] = -1; }
         __syncthreads();
-        const int64_t n_keys = (int64_t)n_flag;
-        double thr = DINF; int pos = 0;                        // lane 0: worst entry of this warp's list
-        const uint4* q4 = reinterpret_cast<const uint4*>(qrow);
-        for (int64_t t = warp; t < n_keys; t += 8) {
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+            const int64_t q = qb + i;
+            if (q >= nq) continue;
+            if (!q_ok[i]) {
+                for (int e = threadIdx.x; e < KP; e += 256) { extra_idx[q * KP + e] = -1; extra_d2[q * KP + e] = DINF; }
+                continue;
+            }
+            const __half* src = op + (q_row0 + q) * ld;
+            for (int c = threadIdx.x; c < dp; c += 256) qrows[i * dp + c] = (uint32_t)__half2float(src[c]);
+        }
+        for (int e = threadIdx.x; e < 8 * QB * KP; e += 256) { (&wl_d[0][0][0])[e] = DINF; (&wl_i[0][0][0])[e] = -1; }
+        __syncthreads();
+        // lane i < QB keeps the list of query i of this warp: worst entry (value, position) in registers
+        double thr = DINF; int pos = 0;
+        const bool mine = lane < QB && q_ok[lane < QB ? lane : 0] && qb + lane < nq;
+        for (int64_t t = warp; t < n_flag; t += 8) {
             const int32_t j = flag_rows[t];
             const kb_rowmeta mj = rowmeta[j];
             if (mj.flags & 8) continue;                        // padding row of a multi-rank gather
-            // exact integer Gram entry g = sum_c a_c*b_c (u32 x u32 -> u64 multiply-adds; a 200 kb homopolymer against
-            // itself stays below 2^36): one integer instruction per column instead of an fp64 difference and square
-            unsigned long long g = 0;
-            if (mj.flags & 3) {
-                const int slot = (int)t;                       // keys are the flagged rows, in flag_rows order
-                if (slot >= 0) {
-                    const uint32_t* krow = flag_counts + (int64_t)slot * ld_fc;
-                    const int nc = fc_cols < dp ? fc_cols : dp;
-                    if ((ld_fc & 3) == 0 && (reinterpret_cast<uintptr_t>(flag_counts) & 15) == 0) {
-                        const uint4* k4 = reinterpret_cast<const uint4*>(krow);
-                        const int n4 = nc >> 2;
-                        for (int c = lane; c < n4; c += 32) {
-                            const uint4 b = __ldg(k4 + c); const uint4 a = q4[c];
-                            g += (unsigned long long)a.x * b.x; g += (unsigned long long)a.y * b.y;
-                            g += (unsigned long long)a.z * b.z; g += (unsigned long long)a.w * b.w;
-                        }
-                        for (int c = (n4 << 2) + lane; c < nc; c += 32) g += (unsigned long long)qrow[c] * __ldg(krow + c);
-                    } else {
-                        for (int c = lane; c < nc; c += 32) g += (unsigned long long)qrow[c] * __ldg(krow + c);
-                    }
-                }
-            } else {
-                const uint4* k8 = reinterpret_cast<const uint4*>(op + (int64_t)j * ld);   // 8 fp16 counts (exact integers <= 2048)
-                for (int c = lane; c < (dp >> 3); c += 32) {
-                    const uint4 b = __ldg(k8 + c);
-                    const uint4 a0 = q4[2 * c], a1 = q4[2 * c + 1];
-                    const __half2* hb = reinterpret_cast<const __half2*>(&b);
-                    const float2 b0 = __half22float2(hb[0]), b1 = __half22float2(hb[1]), b2 = __half22float2(hb[2]), b3 = __half22float2(hb[3]);
-                    g += (unsigned long long)a0.x * (uint32_t)b0.x; g += (unsigned long long)a0.y * (uint32_t)b0.y;
-                    g += (unsigned long long)a0.z * (uint32_t)b1.x; g += (unsigned long long)a0.w * (uint32_t)b1.y;
-                    g += (unsigned long long)a1.x * (uint32_t)b2.x; g += (unsigned long long)a1.y * (uint32_t)b2.y;
-                    g += (unsigned long long)a1.z * (uint32_t)b3.x; g += (unsigned long long)a1.w * (uint32_t)b3.y;
+            // exact integer Gram entries g_i = sum_c a_ic*b_c (u32 x u32 -> u64 multiply-adds)
+            unsigned long long g[QB];
+#pragma unroll
+            for (int i = 0; i < QB; ++i) g[i] = 0ull;
+            const uint32_t* krow = flag_counts + t * ld_fc;    // keys are the flagged rows, in flag_rows order
+            const uint4* k4 = reinterpret_cast<const uint4*>(krow);
+            for (int c = lane; c < n4; c += 32) {
+                const uint4 b = __ldg(k4 + c);
+#pragma unroll
+                for (int i = 0; i < QB; ++i) {
+                    const uint4 a = reinterpret_cast<const uint4*>(qrows + i * dp)[c];
+                    g[i] += (unsigned long long)a.x * b.x; g[i] += (unsigned long long)a.y * b.y;
+                    g[i] += (unsigned long long)a.z * b.z; g[i] += (unsigned long long)a.w * b.w;
                 }
             }
-            for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-            if (lane == 0) {
-                const double d2 = kb_d2_from_gram(mq.sqnorm, mq.key_len, mj.sqnorm, mj.key_len, g);
-                if (d2 < thr || (d2 == thr && wl_i[warp][pos] < 0)) {
-                    wl_d[warp][pos] = d2; wl_i[warp][pos] = j;
+            for (int c = (n4 << 2) + lane; c < nc; c += 32) {
+                const uint32_t b = __ldg(krow + c);
+#pragma unroll
+                for (int i = 0; i < QB; ++i) g[i] += (unsigned long long)qrows[i * dp + c] * b;
+            }
+#pragma unroll
+            for (int i = 0; i < QB; ++i)
+                for (int o = 16; o > 0; o >>= 1) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
+            if (mine) {
+                unsigned long long gm = g[0];
+#pragma unroll
+                for (int i = 1; i < QB; ++i) if (lane == i) gm = g[i];
+                const double d2 = kb_d2_from_gram(q_n[lane], q_l[lane], mj.sqnorm, mj.key_len, gm);
+                if (d2 < thr || (d2 == thr && wl_i[warp][lane][pos] < 0)) {
+                    wl_d[warp][lane][pos] = d2; wl_i[warp][lane][pos] = j;
                     double m = -1.0; int mp = 0;
                     for (int e = 0; e < KP; ++e) {
-                        const double x = wl_i[warp][e] < 0 ? DINF : wl_d[warp][e];
+                        const double x = wl_i[warp][lane][e] < 0 ? DINF : wl_d[warp][lane][e];
                         if (x > m) { m = x; mp = e; }
                     }
                     thr = m; pos = mp;
@@ -778,13 +789,14 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
             }
         }
         __syncthreads();
-        // merge the 8 warp lists: KP rounds of arg-min over 8*KP entries by one warp
-        if (warp == 0) {
+        // merge the 8 warp lists of query `warp` (warps 0..QB-1): KP rounds of arg-min over 8*KP entries
+        if (warp < QB && q_ok[warp] && qb + warp < nq) {
+            const int64_t q = qb + warp;
             for (int r = 0; r < KP; ++r) {
                 double best = DINF; int32_t bi = 0x7fffffff; int bslot = -1;
                 for (int e = lane; e < 8 * KP; e += 32) {
-                    const int32_t ii = wl_i[e / KP][e % KP];
-                    const double dd = wl_d[e / KP][e % KP];
+                    const int32_t ii = wl_i[e / KP][warp][e % KP];
+                    const double dd = wl_d[e / KP][warp][e % KP];
                     if (ii >= 0 && (dd < best || (dd == best && ii < bi))) { best = dd; bi = ii; bslot = e; }
                 }
                 for (int o = 16; o > 0; o >>= 1) {
@@ -796,7 +808,7 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
                 if (lane == 0) {
                     extra_idx[q * KP + r] = (bslot >= 0) ? bi : -1;
                     extra_d2[q * KP + r] = (bslot >= 0) ? best : DINF;
-                    if (bslot >= 0) wl_i[bslot / KP][bslot % KP] = -1;
+                    if (bslot >= 0) wl_i[bslot / KP][warp][bslot % KP] = -1;
                 }
                 __syncwarp();
             }
@@ -818,56 +830,92 @@ k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta*
         const int32_t* __restrict__ flag_rows, const uint32_t* __restrict__ flag_counts, int64_t ld_fc,
         int32_t fc_cols, int32_t n_flag, int64_t keys_per_cta,
         double* __restrict__ d2_out, int32_t* __restrict__ idx_out) {
-    extern __shared__ __align__(16) float qs[];               // K6_QB x dp query counts as floats (exact: <= 2^24)
+    // K6_QB x dp query counts: as floats (exact <= 2^24) when no listed row of this CTA is flagged -- then the fp32 dot
+    // product against an ordinary key IS the exact integer Gram entry --, as u32 when one is (integer path for every key)
+    extern __shared__ __align__(16) float qs[];
+    uint32_t* qu = reinterpret_cast<uint32_t*>(qs);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t b0 = (int64_t)blockIdx.x * K6_QB;           // first listed row of this CTA (relative to row_lo)
     const double DINF = __longlong_as_double(0x7ff0000000000000LL);
     int32_t selfs[K6_QB]; double lqs[K6_QB], nqs[K6_QB]; bool qf[K6_QB], live[K6_QB];
+    bool cta_f = false;
 #pragma unroll
     for (int i = 0; i < K6_QB; ++i) {
         live[i] = b0 + i < n_rows;
         selfs[i] = live[i] ? (int32_t)(q_row0 + rows[row_lo + b0 + i]) : 0;
         const kb_rowmeta m = rowmeta[selfs[i]];
-        lqs[i] = (double)m.key_len; nqs[i] = m.sqnorm; qf[i] = (m.flags & 3) != 0;
+        lqs[i] = (double)m.key_len; nqs[i] = m.sqnorm; qf[i] = live[i] && (m.flags & 3) != 0;
+        cta_f |= qf[i];
+    }
+#pragma unroll
+    for (int i = 0; i < K6_QB; ++i) {
         if (qf[i]) {
             const int slot = find_slot(flag_rows, n_flag, selfs[i]);
             for (int c = threadIdx.x; c < dp; c += 256)
-                qs[i * dp + c] = (slot >= 0 && c < fc_cols) ? (float)flag_counts[(int64_t)slot * ld_fc + c] : 0.f;
+                qu[i * dp + c] = (slot >= 0 && c < fc_cols) ? flag_counts[(int64_t)slot * ld_fc + c] : 0u;
+        } else if (cta_f) {
+            for (int c = threadIdx.x; c < dp; c += 256) qu[i * dp + c] = (uint32_t)__half2float(op[(int64_t)selfs[i] * ld + c]);
         } else {
             for (int c = threadIdx.x; c < dp; c += 256) qs[i * dp + c] = __half2float(op[(int64_t)selfs[i] * ld + c]);
         }
     }
     __syncthreads();
+    const bool fvec = (ld_fc & 3) == 0 && (reinterpret_cast<uintptr_t>(flag_counts) & 15) == 0;
+    const int nfc = fc_cols < dp ? fc_cols : dp;
     const int64_t j_lo = (int64_t)blockIdx.y * keys_per_cta;
     const int64_t j_hi = (j_lo + keys_per_cta < nk) ? j_lo + keys_per_cta : nk;
     for (int64_t j = j_lo + warp; j < j_hi; j += 8) {
         const kb_rowmeta mj = rowmeta[j];
         const bool kf = (mj.flags & 3) != 0;
         const bool pad = (mj.flags & 8) != 0;
-        const double lj = (double)mj.key_len;
-        double acc[K6_QB];
+        const bool any_f = kf || cta_f;
+        unsigned long long gi[K6_QB];                         // exact Gram entries (after the reduction: in every lane)
 #pragma unroll
-        for (int i = 0; i < K6_QB; ++i) acc[i] = 0.0;
-        bool any_f = kf;
-#pragma unroll
-        for (int i = 0; i < K6_QB; ++i) any_f |= qf[i];
+        for (int i = 0; i < K6_QB; ++i) gi[i] = 0ull;
         if (!pad) {
             if (any_f) {
                 // a flagged row is involved: exact 64-bit integer Gram entries from the true counts
-                unsigned long long gi[K6_QB];
+                if (kf) {
+                    const int slot = find_slot(flag_rows, n_flag, (int32_t)j);
+                    if (slot >= 0) {
+                        const uint32_t* krow = flag_counts + (int64_t)slot * ld_fc;
+                        const int n4 = (fvec && cta_f) ? (nfc >> 2) : 0;
+                        const uint4* k4 = reinterpret_cast<const uint4*>(krow);
+                        for (int c = lane; c < n4; c += 32) {
+                            const uint4 b = __ldg(k4 + c);
 #pragma unroll
-                for (int i = 0; i < K6_QB; ++i) gi[i] = 0ull;
-                const int slot = kf ? find_slot(flag_rows, n_flag, (int32_t)j) : -1;
-                for (int c = lane; c < dp; c += 32) {
-                    const uint32_t b = kf ? ((slot >= 0 && c < fc_cols) ? flag_counts[(int64_t)slot * ld_fc + c] : 0u)
-                                          : (uint32_t)__half2float(op[j * ld + c]);
+                            for (int i = 0; i < K6_QB; ++i) {
+                                const uint4 a = reinterpret_cast<const uint4*>(qu + i * dp)[c];
+                                gi[i] += (unsigned long long)a.x * b.x; gi[i] += (unsigned long long)a.y * b.y;
+                                gi[i] += (unsigned long long)a.z * b.z; gi[i] += (unsigned long long)a.w * b.w;
+                            }
+                        }
+                        for (int c = (n4 << 2) + lane; c < nfc; c += 32) {
+                            const uint32_t b = __ldg(krow + c);
 #pragma unroll
-                    for (int i = 0; i < K6_QB; ++i) gi[i] += (unsigned long long)__float2uint_rn(qs[i * dp + c]) * b;
-                }
+                            for (int i = 0; i < K6_QB; ++i)
+                                gi[i] += (unsigned long long)(cta_f ? qu[i * dp + c] : __float2uint_rn(qs[i * dp + c])) * b;
+                        }
+                    }
+                } else {
+                    // ordinary key (fp16 counts, exact integers <= 2048) against u32 query rows: 8 columns per load
+                    const uint4* k8 = reinterpret_cast<const uint4*>(op + j * ld);
+                    for (int c = lane; c < (dp >> 3); c += 32) {
+                        const uint4 b = __ldg(k8 + c);
+                        const __half2* hb = reinterpret_cast<const __half2*>(&b);
+                        const float2 f0 = __half22float2(hb[0]), f1 = __half22float2(hb[1]), f2 = __half22float2(hb[2]), f3 = __half22float2(hb[3]);
+                        const uint32_t b0 = (uint32_t)f0.x, b1 = (uint32_t)f0.y, b2 = (uint32_t)f1.x, b3 = (uint32_t)f1.y;
+                        const uint32_t b4 = (uint32_t)f2.x, b5 = (uint32_t)f2.y, b6 = (uint32_t)f3.x, b7 = (uint32_t)f3.y;
 #pragma unroll
-                for (int i = 0; i < K6_QB; ++i) {
-                    for (int o = 16; o > 0; o >>= 1) gi[i] += __shfl_xor_sync(0xffffffffu, gi[i], o);
-                    acc[i] = kb_d2_from_gram(nqs[i], (int32_t)lqs[i], mj.sqnorm, mj.key_len, gi[i]);   // d2 itself
+                        for (int i = 0; i < K6_QB; ++i) {
+                            const uint4 a0 = reinterpret_cast<const uint4*>(qu + i * dp)[2 * c];
+                            const uint4 a1 = reinterpret_cast<const uint4*>(qu + i * dp)[2 * c + 1];
+                            gi[i] += (unsigned long long)a0.x * b0; gi[i] += (unsigned long long)a0.y * b1;
+                            gi[i] += (unsigned long long)a0.z * b2; gi[i] += (unsigned long long)a0.w * b3;
+                            gi[i] += (unsigned long long)a1.x * b4; gi[i] += (unsigned long long)a1.y * b5;
+                            gi[i] += (unsigned long long)a1.z * b6; gi[i] += (unsigned long long)a1.w * b7;
+                        }
+                    }
                 }
             } else {
                 // unflagged x unflagged: the fp32 dot product is the exact integer Gram entry
@@ -889,28 +937,24 @@ k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta*
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < K6_QB; ++i) acc[i] = (double)g[i];
+                for (int i = 0; i < K6_QB; ++i) gi[i] = (unsigned long long)g[i];   // per-lane partial sums are exact integers
             }
         }
-        if (!any_f) {
 #pragma unroll
-            for (int i = 0; i < K6_QB; ++i)
-                for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        }
-        if (lane == 0) {
+        for (int i = 0; i < K6_QB; ++i)
+            for (int o = 16; o > 0; o >>= 1) gi[i] += __shfl_xor_sync(0xffffffffu, gi[i], o);
+        if (lane < K6_QB) {
+            // lane i finishes listed row i
+            unsigned long long gm = gi[0]; double nq_ = nqs[0], lq_ = lqs[0]; int32_t self_ = selfs[0]; bool live_ = live[0];
 #pragma unroll
-            for (int i = 0; i < K6_QB; ++i) {
-                if (!live[i]) continue;
+            for (int i = 1; i < K6_QB; ++i) if (lane == i) { gm = gi[i]; nq_ = nqs[i]; lq_ = lqs[i]; self_ = selfs[i]; live_ = live[i]; }
+            if (live_) {
                 double d2;
                 if (pad) d2 = DINF;
-                else if ((int32_t)j == selfs[i]) d2 = -1.0;                   // the point itself sorts first
-                else if (any_f) d2 = acc[i];
-                else {
-                    const double num = lj * lj * nqs[i] + lqs[i] * lqs[i] * mj.sqnorm - 2.0 * (lj * lqs[i]) * acc[i];
-                    d2 = num / ((lqs[i] * lj) * (lqs[i] * lj));
-                }
-                d2_out[(b0 + i) * nk + j] = d2;
-                idx_out[(b0 + i) * nk + j] = (int32_t)j;
+                else if ((int32_t)j == self_) d2 = -1.0;                      // the point itself sorts first
+                else d2 = kb_d2_from_gram(nq_, (int32_t)lq_, mj.sqnorm, mj.key_len, gm);
+                d2_out[(b0 + lane) * nk + j] = d2;
+                idx_out[(b0 + lane) * nk + j] = (int32_t)j;
             }
         }
     }
@@ -981,20 +1025,29 @@ int run_rerank(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, in
     return KB_OK;
 }
 
-template <int KP>
-int run_exact(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp, const kb_rowmeta* rowmeta,
-              int64_t nk, int64_t q_row0, int64_t nq, const int32_t* flag_rows, const uint32_t* flag_counts,
-              int64_t ld_fc, int32_t fc_cols, int32_t n_flag, uint8_t* ws) {
-    auto kern = k4x_exact<KP>;
-    const size_t smem = (size_t)dp * sizeof(uint32_t);
+template <int KP, int QB>
+int launch_exact(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp, const kb_rowmeta* rowmeta,
+                 int64_t nk, int64_t q_row0, int64_t nq, const int32_t* flag_rows, const uint32_t* flag_counts,
+                 int64_t ld_fc, int32_t fc_cols, int32_t n_flag, uint8_t* ws) {
+    auto kern = k4x_exact<KP, QB>;
+    const size_t smem = (size_t)QB * dp * sizeof(uint32_t);
     KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t grid = nq < (int64_t)ctx->sm_count * 8 ? nq : (int64_t)ctx->sm_count * 8;
+    const int64_t blocks = (nq + QB - 1) / QB;
+    const int64_t grid = blocks < (int64_t)ctx->sm_count * 8 ? blocks : (int64_t)ctx->sm_count * 8;
     kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(op, ld, dp, rowmeta, nk, q_row0, nq, flag_rows, flag_counts, ld_fc,
                                                      fc_cols, n_flag, reinterpret_cast<int32_t*>(ws + p.off_xidx),
                                                      reinterpret_cast<double*>(ws + p.off_xd2));
     ctx->launches++;
     KB_CUDA(cudaGetLastError());
     return KB_OK;
+}
+
+template <int KP>
+int run_exact(kb_ctx* ctx, const KbKnnPlan& p, const __half* op, int64_t ld, int32_t dp, const kb_rowmeta* rowmeta,
+              int64_t nk, int64_t q_row0, int64_t nq, const int32_t* flag_rows, const uint32_t* flag_counts,
+              int64_t ld_fc, int32_t fc_cols, int32_t n_flag, uint8_t* ws) {
+    if ((size_t)4 * dp * sizeof(uint32_t) <= 160 * 1024) return launch_exact<KP, 4>(ctx, p, op, ld, dp, rowmeta, nk, q_row0, nq, flag_rows, flag_counts, ld_fc, fc_cols, n_flag, ws);
+    return launch_exact<KP, 1>(ctx, p, op, ld, dp, rowmeta, nk, q_row0, nq, flag_rows, flag_counts, ld_fc, fc_cols, n_flag, ws);
 }
 
 #define KB_KP_SWITCH(kp, CALL)                 \

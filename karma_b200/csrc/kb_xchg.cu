@@ -4,9 +4,9 @@
 // records of ALL contigs before it can score its own query rows against them, and every rank wants the
 // finished k-lists.  Instead of collectives, every rank owns one "arena" (cudaMalloc + CUDA IPC, the same
 // layout on every rank) that its peers map:
-//   * after K3 a rank pushes its shard of each gathered array into every peer's arena on a side stream, nearest-
-//     following rank first, and raises arrive[rank] = epoch there as each shard completes (kx_push_sm: SM stores
-//     over NVLink next to the running K4; copy engines for two ranks);
+//   * after K3 a rank pushes its shard of each gathered array into every peer's arena on a side stream (copy engines,
+//     three peers at a time), nearest-following rank first, and raises arrive[rank] = epoch there as each shard
+//     completes (KB_XCHG_SM=1 selects kx_push_sm instead: SM stores over NVLink next to the running K4 -- measured slower);
 //   * K4 (kb_knn_tc.cu) starts on the local shard at once; its TMA producer polls arrive[r] before the first
 //     key tile of rank r, so the transfer overlaps the sweep tile by tile;
 //   * K5 stores its rows straight into every peer's gathered result arrays (stores over NVLink);
@@ -96,11 +96,10 @@ __global__ void kx_signal_arrive(const uint8_t* local, uint8_t* peer_arena, int 
     __threadfence_system();
     st_release_sys(&reinterpret_cast<KbXchgCtrl*>(peer_arena)->arrive[rank], e);
 }
-// Shards pushed by the SMs: every destination in turn (nearest-following rank first, the order in which K4 sweeps)
-// gets this rank's shard of every region with the WHOLE grid storing to it over NVLink, so the shard K4 needs first
-// lands first and at full link rate; the last CTA to finish a destination raises its arrival flag.  (Peer copies on
-// the copy engines move ~150 GB/s per stream and run three at a time: at 4 and 8 ranks the sweep then waits for data.)
-// The kernel runs NEXT TO the persistent K4 CTAs (no shared memory, 32 registers): it must never need an SM of its own.
+// Optional (KB_XCHG_SM=1): shards pushed by the SMs.  Every destination in turn (nearest-following rank first, the order
+// in which K4 sweeps) gets this rank's shard of every region with the WHOLE grid storing to it over NVLink; the last CTA
+// to finish a destination raises its arrival flag.  The kernel runs NEXT TO the persistent K4 CTAs (no shared memory):
+// it must never need an SM of its own.  Not the default: see kb_xchg_create.
 struct KxRegions { int n; int64_t off[4]; int64_t bytes[4]; };
 
 __global__ void __launch_bounds__(256)
@@ -184,11 +183,12 @@ extern "C" int kb_xchg_create(kb_ctx* ctx, int world, int rank, int64_t bytes, k
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void**)&x->d_count, sizeof(uint32_t) * KB_XCHG_MAX_WORLD);
     if (e == cudaSuccess) e = cudaMemset(x->d_count, 0, sizeof(uint32_t) * KB_XCHG_MAX_WORLD);
-    {   // KB_XCHG_SM=0: copy engines (experiments / fallback for platforms without peer stores); default: SM push for 3+ ranks
+    {   // KB_XCHG_SM=1: push the shards with a kernel (kx_push_sm) instead of the copy engines.  Measured on 8 x B200, 50k contigs:
+        // 0.775 ms per pass against 0.626 ms with the copy engines -- the push finishes at the same time either way (0.31-0.37 ms
+        // into the pass), but the kernel's CTAs take issue slots and L2 bandwidth from the persistent K4 CTAs they run next to.
         const char* f = getenv("KB_XCHG_SM");
-        x->sm_push = f ? (atoi(f) != 0) : (world > 2);
+        x->sm_push = f ? (atoi(f) != 0) : 0;
     }
-    if (e != cudaSuccess) { cudaFree(x->local); cudaFree(x->d_peer); free(x); return kb_cuda_fail(e, "arena set-up (copy streams)"); }
     x->peer[rank] = x->local;
     *out = x; *d_local = x->local;
     return KB_OK;
