@@ -811,6 +811,20 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def host_chunks(offsets, chunks):
+    """Row chunks of about equal bases for the host-to-host pass: [(row_lo, row_hi, byte_lo, byte_hi)], covering every
+    row once, in order; at most ``chunks`` of them and none for fewer than ~1024 rows each."""
+    on = np.asarray(offsets, dtype=np.int64)
+    n = len(on) - 1
+    total = int(on[-1])
+    c = max(1, min(int(chunks), n // 1024 if n >= 2048 else 1))
+    cuts = [0] + [int(np.searchsorted(on, total * i / c)) for i in range(1, c)] + [n]
+    cuts = sorted(set(min(max(x, 0), n) for x in cuts))
+    if len(cuts) == 1:
+        cuts = [0, n]
+    return [(lo, hi, int(on[lo]), int(on[hi])) for lo, hi in zip(cuts[:-1], cuts[1:])]
+
+
 class PassPlan:
     """The optimistic hot path (K1 -> K3 -> exchange -> K4 -> K5) of `_device_pass`, planned once for a shape and
     then re-run with ONE enqueue: every buffer is static, nothing is allocated and nothing synchronises inside
@@ -1104,14 +1118,7 @@ class PassPlan:
             io["h_offsets"].copy_(o)
         if self.n and t(key_len, np.int32).data_ptr() != io["h_key_len"].data_ptr():
             io["h_key_len"].copy_(t(key_len, np.int32))
-        # row chunks of about equal bases; byte bounds widened to 16 so that every copy is aligned
-        on = io["h_offsets"].numpy()
-        c = max(1, min(int(chunks), self.n // 1024 if self.n >= 2048 else 1))
-        cuts = [0] + [int(np.searchsorted(on, total * i / c)) for i in range(1, c)] + [self.n]
-        cuts = sorted(set(min(max(x, 0), self.n) for x in cuts))
-        if len(cuts) == 1:
-            cuts = [0, self.n]
-        plan = [(lo, hi, int(on[lo]), int(on[hi])) for lo, hi in zip(cuts[:-1], cuts[1:])]
+        plan = host_chunks(io["h_offsets"].numpy(), chunks)
         if plan != io["chunks"]:
             io["chunks"] = plan
             io["graph"] = None

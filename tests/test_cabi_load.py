@@ -181,3 +181,32 @@ def test_knn_piece_table_covers_every_tile_once(lib, nq, nk, q0, dp, k):
     if nk * dp * 2 > 120e6 and n_tiles >= 2:
         # a key set beyond the L2 is swept in whole bands, dealt round-robin, so that concurrent clusters share key tiles
         assert info["kind"] == 0 and info["bands"] >= 2 and (pieces[:, 5] == 0).all() and (pieces[:, 6] == pieces[:, 3]).all()
+
+
+@pytest.mark.parametrize("nq,nk,q0,dp,k", [(25000, 50000, 25000, 1088, 2), (12500, 50000, 12500, 1088, 2), (6250, 50000, 43750, 1088, 15),
+                                           (6250, 50000, 0, 1088, 2), (62500, 500000, 187500, 5120, 15), (257, 700, 300, 1088, 5)])
+def test_shard_sweeps_follow_the_arrival_order(lib, nq, nk, q0, dp, k):
+    """A query shard receives the other shards over NVLink in the order q+1, q+2, ..., q-1.  Every query group must
+    therefore sweep the key tiles as ONE rotation that starts on a tile lying fully inside the local rows and runs upwards
+    with wrap-around -- the tile straddling the start of the local shard (it needs rows of rank q-1) comes after all others."""
+    import numpy as np
+    info, pieces, start, slots, groups = _plan(lib, nq, nk, q0, dp, k)
+    n_tiles = -(-nk // 256)
+    first_full = -(-q0 // 256)
+    last_full = (q0 + nq) // 256 - 1
+    per_group = {}
+    for g, slot, t_lo, cnt, shift, i_lo, i_cnt, _ in pieces:
+        i = np.arange(i_lo, i_lo + i_cnt) + shift
+        tiles = (np.where(i >= cnt, i - cnt, i) + t_lo) % n_tiles
+        per_group.setdefault(int(g), []).append((int(slot), tiles))
+    for g, lst in per_group.items():
+        seq = np.concatenate([t for _, t in sorted(lst, key=lambda x: x[0])])      # slots are handed out in sweep order
+        assert len(seq) == n_tiles
+        assert ((seq[1:] - seq[:-1]) % n_tiles == 1).all(), (g, seq[:8])
+        if first_full <= last_full:
+            assert first_full <= seq[0] <= last_full, (g, seq[0], first_full, last_full)
+            if q0 % 256:
+                # the head straddler is behind every tile of the other shards
+                pos = int(np.flatnonzero(seq == first_full - 1)[0])
+                foreign = [int(np.flatnonzero(seq == t)[0]) for t in range(n_tiles) if t < first_full - 1 or t > last_full + 1]
+                assert not foreign or pos > max(foreign)

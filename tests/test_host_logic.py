@@ -287,3 +287,25 @@ def test_knn_oracle_exact_vs_fp64():
     bad[0, -1] = (set(range(40)) - set(i_f[0].tolist())).pop()
     rep = knn_oracle.check_knn(bad, np.sqrt(knn_oracle.d2_fp64(prof)[np.arange(40)[:, None], bad]), knn_oracle.d2_fp64(prof))
     assert not knn_oracle.parity_ok(rep)
+
+
+def test_host_chunks_cover_every_row_once():
+    """Chunk plan of the host-to-host pass (engine.host_chunks): contiguous, complete, balanced by bases."""
+    import numpy as np
+    from karma_b200.engine import host_chunks
+    rng = np.random.default_rng(3)
+    for n, chunks in ((0, 4), (1, 4), (1500, 4), (9000, 1), (9000, 4), (50000, 4), (50000, 7)):
+        lens = rng.integers(200, 15000, size=n)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        plan = host_chunks(off, chunks)
+        assert plan[0][0] == 0 and plan[-1][1] == n and len(plan) <= max(1, chunks)
+        for (lo, hi, b0, b1), nxt in zip(plan, plan[1:] + [None]):
+            assert lo <= hi and b0 == off[lo] and b1 == off[hi]
+            if nxt is not None:
+                assert nxt[0] == hi and hi > lo
+        if n >= 2048 and chunks > 1:
+            assert len(plan) == chunks
+            sizes = [b1 - b0 for _, _, b0, b1 in plan]
+            assert max(sizes) - min(sizes) <= 2 * 15000
+        if n < 2048:
+            assert len(plan) == 1
