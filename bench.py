@@ -14,8 +14,10 @@ A step = one pass of the hot path over the whole assembly.
           karma_b200.engine.PassPlan, a CUDA graph), CUDA-event time, max over ranks.  Step i is
           validated on the host while step i+1 runs.
   e2e   : T1 -- host (pinned) buffers in, host results out through the public API
-          (karma_b200.engine.profile_and_knn): H2D, column dictionary, kernels, D2H of the float64
-          profile and the kNN lists all inside the timed region (wall clock, device-synchronised)
+          (karma_b200.engine.PassPlan.bind_host / run_host): chunked H2D, kernels, exchange, D2H of the float64
+          profile rows, the kNN lists and the validation words of this rank, waited for and validated every
+          step, all inside the timed region (wall clock between barriers, max over ranks).  e2e.single_shot
+          (N=1) is the unplanned call karma_b200.engine.profile_and_knn that KmerClustering makes once per run.
   t2    : T2 -- from the Python dict karma.py builds (marshalling included), N=1 only
 Per-kernel times (stage_ms, roofline) come from a separate eager pass with the library's event pairs on,
 after the timed region.  Supplementary blocks (outside every timed region): the k=15 kernel rate, the
