@@ -818,12 +818,12 @@ k4x_exact(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmet
 
 // ---------------------------------------------------------------------------
 // K6: exact pass over ALL keys for the rows K5 could not certify (and for every row when
-// k > KB_KNN_K_MAX).  k6_dist: one CTA per (4 listed queries, chunk of keys); a warp takes one key
-// row at a time and produces its exact d2 to the 4 queries.  The rows are then ordered by a
-// segmented radix sort on (d2, key index); k6_emit writes the first k of every segment.
+// k > KB_KNN_K_MAX).  k6_dist: one CTA per (K6_QB listed queries, chunk of keys); a warp takes one key
+// row at a time and produces its exact d2 to the K6_QB queries (4; 2 or 1 when four rows of dp counts do not fit the
+// shared memory: -k 7 has 16384 columns).  The rows are then ordered by a segmented radix sort on (d2, key index);
+// k6_emit writes the first k of every segment.
 // ---------------------------------------------------------------------------
-constexpr int K6_QB = 4;
-
+template <int K6_QB>
 __global__ void __launch_bounds__(256)
 k6_dist(const __half* __restrict__ op, int64_t ld, int32_t dp, const kb_rowmeta* __restrict__ rowmeta,
         int64_t nk, int64_t q_row0, const int32_t* __restrict__ rows, int64_t row_lo, int64_t n_rows,
@@ -1239,9 +1239,12 @@ extern "C" int64_t kb_knn_fixup(kb_ctx* ctx, int impl, int32_t k,
     const int32_t* rows = uncert + 4;
     // batches sized for ~1 GB of scratch: (d2 f64 + idx i32) x 2 (sort double buffers) per (row, key)
     int64_t batch = (1LL << 30) / (nk * 24);
-    if (batch < K6_QB) batch = K6_QB;
-    batch = batch / K6_QB * K6_QB;
-    if (batch > n_rows) batch = kb_round_up(n_rows, K6_QB);
+    // listed rows per CTA: as many (4, 2, 1) as fit the shared memory with their dp counts each
+    const int qb = (size_t)4 * d_cols_padded * sizeof(float) <= 200 * 1024 ? 4 : ((size_t)2 * d_cols_padded * sizeof(float) <= 200 * 1024 ? 2 : 1);
+    if ((size_t)qb * d_cols_padded * sizeof(float) > 227 * 1024) { kb_set_error("exact pass: %d columns do not fit the shared memory", (int)d_cols_padded); return KB_EUNSUPPORTED; }
+    if (batch < qb) batch = qb;
+    batch = batch / qb * qb;
+    if (batch > n_rows) batch = kb_round_up(n_rows, qb);
     cudaMemPool_t pool;
     rc = kb_pool_get(ctx, &pool);
     if (rc) return rc;
@@ -1256,21 +1259,26 @@ extern "C" int64_t kb_knn_fixup(kb_ctx* ctx, int impl, int32_t k,
     size_t tmp_bytes = 0;
     cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_bytes, d2a, d2b, ia, ib, (int64_t)cells, (int)batch, seg, seg + 1, 0, 64, st);
     KB_CUDA(cudaMallocFromPoolAsync(&tmp, tmp_bytes ? tmp_bytes : 16, pool, st));
-    const size_t smem = (size_t)K6_QB * d_cols_padded * sizeof(float);
-    KB_CUDA(cudaFuncSetAttribute(k6_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)qb * d_cols_padded * sizeof(float);
+    if (qb == 4) { KB_CUDA(cudaFuncSetAttribute(k6_dist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+    else if (qb == 2) { KB_CUDA(cudaFuncSetAttribute(k6_dist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+    else { KB_CUDA(cudaFuncSetAttribute(k6_dist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
     {
         KbTimer t(ctx, 6);
         for (int64_t lo = 0; lo < n_rows; lo += batch) {
             const int64_t nb = (n_rows - lo < batch) ? n_rows - lo : batch;
-            const int64_t q_ctas = (nb + K6_QB - 1) / K6_QB;
+            const int64_t q_ctas = (nb + qb - 1) / qb;
             int64_t key_ctas = ((int64_t)ctx->sm_count * 8 + q_ctas - 1) / q_ctas;        // enough CTAs to fill the GPU
             if (key_ctas > (nk + 63) / 64) key_ctas = (nk + 63) / 64;
             if (key_ctas < 1) key_ctas = 1;
             if (key_ctas > 65535) key_ctas = 65535;
             const int64_t keys_per_cta = (nk + key_ctas - 1) / key_ctas;
-            k6_dist<<<dim3((unsigned)q_ctas, (unsigned)key_ctas), 256, smem, st>>>(
-                op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, rows, lo, nb, d_flag_rows, d_flag_counts,
-                ld_flag_counts, flag_cols, (int32_t)n_flag, keys_per_cta, d2a, ia);
+#define K6_LAUNCH(QB)                                                                                                 \
+    k6_dist<QB><<<dim3((unsigned)q_ctas, (unsigned)key_ctas), 256, smem, st>>>(                                        \
+        op, ld_operand, d_cols_padded, d_rowmeta, nk, q_row0, rows, lo, nb, d_flag_rows, d_flag_counts,                \
+        ld_flag_counts, flag_cols, (int32_t)n_flag, keys_per_cta, d2a, ia)
+            if (qb == 4) K6_LAUNCH(4); else if (qb == 2) K6_LAUNCH(2); else K6_LAUNCH(1);
+#undef K6_LAUNCH
             ctx->launches++;
             KB_CUDA(cudaGetLastError());
             k6_segments<<<(unsigned)((nb + 256) / 256), 256, 0, st>>>(nk, nb, seg);

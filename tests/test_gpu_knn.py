@@ -149,6 +149,26 @@ def test_exact_side_path_for_rows_beyond_the_tensor_range(engine, k):
     assert res["knn_idx"][240, 1] == 241 and res["knn_idx"][241, 1] == 240
 
 
+def test_exact_side_path_with_wide_rows(engine):
+    """The same side path for -k 7 (16384 columns: four u32 query rows no longer fit the shared memory, K4x then takes one
+    query row per CTA) with homopolymer runs (a count > 2048) among ordinary contigs."""
+    rng = np.random.default_rng(23)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    seqs = list(synth.s1_families(150, seed=4).as_dict().values())
+    seqs += ["A" * 3000, "A" * 2990 + rnd(60), rnd(400) + "C" * 2600, rnd(900)]
+    asm = _assembly_from(seqs)
+    counts, _ = ko.counts_mode(asm.bases, asm.offsets, 7)
+    assert (counts.max(1) > 2048).sum() == 3
+    res = _run(engine, asm, 7, 4, "tc")
+    prof = counts[:, counts.any(0)] / asm.key_len[:, None].astype(np.float64)
+    assert res["profile"].tobytes() == prof.tobytes()
+    rep = knn_oracle.check_knn(res["knn_idx"], res["knn_dist"], knn_oracle.d2_fp64(prof))
+    assert knn_oracle.parity_ok(rep), rep
+    assert res["knn_idx"][150, 1] == 151 and res["knn_idx"][151, 1] == 150
+
+
 def test_dense_5120_k15_at_scale(engine):
     """BASELINE configs 3/4 shape on one GPU at reduced N: 5120 dense columns, n_neighbors=15."""
     asm = synth.s2_redundant(12000, seed=3)
