@@ -51,7 +51,7 @@ def main():
     # the pre-planned pass: peer-memory exchange, three passes back to back (eager, eager, CUDA graph replay);
     # every rank must end up with ALL k-lists, and its own rows must equal the eager / NCCL path bit for bit
     plan_ok = True
-    if not a.exotic and shard.n > 0:
+    if not a.exotic and a.synth != "S3" and shard.n > 0:      # (exotic bytes / flagged rows: the plan reports them, the eager path serves them)
         plan = PassPlan(eng, shard.n, int(shard.offsets[-1]), kmer, n_neighbors=a.neighbors, impl=_lib.KB_KNN_TC,
                         group=dist.group.WORLD, rank=rank, world=world, n_total=asm.n, graph=not a.no_graph)
         plan.load(shard.bases, shard.offsets, shard.key_len)
