@@ -210,3 +210,35 @@ def test_shard_sweeps_follow_the_arrival_order(lib, nq, nk, q0, dp, k):
                 pos = int(np.flatnonzero(seq == first_full - 1)[0])
                 foreign = [int(np.flatnonzero(seq == t)[0]) for t in range(n_tiles) if t < first_full - 1 or t > last_full + 1]
                 assert not foreign or pos > max(foreign)
+
+
+def test_knn_piece_table_random_shapes(lib):
+    """Randomised shapes (ragged shards of 1..8 ranks, arbitrary query sub-ranges, 8..148 SMs, every list width): every
+    (query group, key tile) pair exactly once, every piece in its own candidate slot, at most 512 candidates per row."""
+    import random
+    import numpy as np
+    rnd = random.Random(5)
+    for _ in range(120):
+        nk = rnd.choice([600, 1000, 3000, 7777, 20011, 50000, 123457])
+        world = rnd.choice([1, 2, 3, 4, 5, 8])
+        per = -(-nk // world)
+        q0 = min(rnd.randrange(world) * per, nk - 1)
+        nq = max(1, min(per, nk - q0))
+        if rnd.random() < 0.2:
+            q0 = rnd.randrange(0, nk)
+            nq = rnd.randrange(1, nk - q0 + 1)
+        dp = rnd.choice([64, 1088, 1280, 5120])
+        k = min(rnd.choice([1, 2, 5, 15, 24, 40, 60]), nk)
+        sm = rnd.choice([148, 132, 8])
+        info, pieces, start, slots, groups = _plan(lib, nq, nk, q0, dp, k, sm)
+        n_tiles = -(-nk // 256)
+        cover = np.zeros((groups, n_tiles), dtype=np.int32)
+        seen = set()
+        for g, slot, t_lo, cnt, shift, i_lo, i_cnt, _pad in pieces:
+            assert (g, slot) not in seen and 0 <= slot < slots[g] <= info["slots"]
+            seen.add((g, slot))
+            assert 0 <= i_lo and i_lo + i_cnt <= cnt and i_cnt >= 1 and 0 <= shift < cnt and 0 <= t_lo < n_tiles
+            i = np.arange(i_lo, i_lo + i_cnt) + shift
+            cover[g, (np.where(i >= cnt, i - cnt, i) + t_lo) % n_tiles] += 1
+        assert (cover == 1).all(), (nq, nk, q0, dp, k, sm, info)
+        assert info["slots"] * info["kp"] <= 512
